@@ -1,0 +1,597 @@
+// wbc_kernels.cu -- kernels + C ABI of libwbc_b200.so (see include/wbc_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include "wbc_step.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+#define CUDA_TRY(expr)                                                          \
+  do {                                                                          \
+    cudaError_t e__ = (expr);                                                   \
+    if (e__ != cudaSuccess) return fail(WBC_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+struct WbcModel {
+  DevModel host;
+  DevModel* dev;
+  int device;
+  int sm_count;
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_model(const DevModel* __restrict__ g, DevModel* s) {
+  const int nwords = sizeof(DevModel) / 4;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(s);
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// fused tick / assembly accessor: persistent CTAs, one state per warp
+template <int NV, bool DEBUG_OUT>
+__global__ void __launch_bounds__(384, 1) wbc_step_kernel(const __grid_constant__ StepParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
+  stage_model(P.model, Ms);
+  const StepLayout L = step_layout(NV, P.nC);
+  const int warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
+  for (long long s = (long long)blockIdx.x * wpc + warp; s < P.N; s += (long long)gridDim.x * wpc) {
+    warp_wbc_step<NV, DEBUG_OUT>(P, Ms, ws, L, s);
+    __syncwarp();
+  }
+}
+
+// FK + frame Jacobians accessor (HBM-write bound): one state per warp
+struct FkJacParams {
+  const DevModel* model;
+  const double* q;
+  long long N;
+  int nsel, rf;
+  int slots[WBC_MAX_FRAMES];
+  double* out_oMf;
+  double* out_J;
+  double* out_oMi;   // joint_jacobians variant
+  double* out_Jw;
+};
+
+__global__ void __launch_bounds__(256) wbc_fk_jac_kernel(const __grid_constant__ FkJacParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
+  stage_model(P.model, Ms);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int per_warp = WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40;
+  double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * per_warp;
+  double* oMi = ws;
+  double* oMf = ws + WBC_MAX_JOINTS * WBC_T_STRIDE;
+  double* qs = oMf + WBC_MAX_FRAMES * WBC_T_STRIDE;
+  const int nq = Ms->nq, nv = Ms->nv, nj = Ms->njoints;
+  for (long long s = (long long)blockIdx.x * wpc + warp; s < P.N; s += (long long)gridDim.x * wpc) {
+    for (int i = lane; i < nq; i += 32) qs[i] = P.q[s * nq + i];
+    __syncwarp();
+    warp_fk(Ms, qs, oMi, lane);
+    warp_frames(Ms, oMi, oMf, lane);
+    double Sc[6];
+    warp_jac_column(Ms, oMi, lane, Sc);
+    if (P.out_oMi) {
+      for (int i = lane; i < nj * 12; i += 32) {
+        const int j = i / 12, e = i % 12;
+        double v = oMi[j * WBC_T_STRIDE + e];
+        if (j == 0) v = (e == 0 || e == 4 || e == 8) ? 1.0 : 0.0;
+        P.out_oMi[s * nj * 12 + i] = v;
+      }
+    }
+    if (P.out_Jw && lane < nv)
+      for (int r = 0; r < 6; ++r) P.out_Jw[(s * 6 + r) * nv + lane] = Sc[r];
+    for (int f = 0; f < P.nsel; ++f) {
+      const int slot = P.slots[f];
+      const double* T = oMf + slot * WBC_T_STRIDE;
+      if (P.out_oMf && lane < 12) P.out_oMf[(s * P.nsel + f) * 12 + lane] = T[lane];
+      if (P.out_J && lane < nv) {
+        double Jc[6];
+        frame_jac_column(Sc, Ms->frame_supp[slot], lane, T, P.rf, Jc);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) P.out_J[((s * P.nsel + f) * 6 + r) * nv + lane] = Jc[r];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// initialiseWBC snapshot (Robot_Wrapper4.py:354-383)
+__global__ void __launch_bounds__(256) wbc_init_memory_kernel(const DevModel* __restrict__ model, const double* __restrict__ q,
+                                                              long long N, double* __restrict__ mem, double* __restrict__ ref) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
+  stage_model(model, Ms);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int per_warp = WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40;
+  double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * per_warp;
+  double* oMi = ws;
+  double* oMf = ws + WBC_MAX_JOINTS * WBC_T_STRIDE;
+  double* qs = oMf + WBC_MAX_FRAMES * WBC_T_STRIDE;
+  const int nq = Ms->nq;
+  for (long long s = (long long)blockIdx.x * wpc + warp; s < N; s += (long long)gridDim.x * wpc) {
+    for (int i = lane; i < nq; i += 32) qs[i] = q[s * nq + i];
+    __syncwarp();
+    warp_fk(Ms, qs, oMi, lane);
+    warp_frames(Ms, oMi, oMf, lane);
+    double* m = mem + s * WBC_MEM_STRIDE;
+    double* r = ref + s * WBC_REF_STRIDE;
+    const double* Tt = oMf + WBC_FRAME_TRUNK * WBC_T_STRIDE;
+    if (lane < 6) {
+      const double* T = oMf + lane * WBC_T_STRIDE;
+      double Rf[9], qf[4], eul[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rf[i] = T[i];
+      scipy_quat_from_matrix(Rf, qf);
+      scipy_euler_xyz_from_quat(qf, eul);
+      if (lane < 5) {
+        for (int i = 0; i < 3; ++i) {
+          m[MEM_PREV_EE_POS + 3 * lane + i] = T[9 + i];              // prev_EE_pos (:373)
+          r[REF_DEF_EE_ORI + 3 * lane + i] = eul[i];                 // default_EE_ori_list (:365-367)
+        }
+        double Rt[9], Rrel[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rt[i] = Tt[i];
+        // prev_EE_CoM_rot = trunk_R^T * EE_R (:374-376)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) Rrel[3 * i + j] = Rt[i] * Rf[j] + Rt[3 + i] * Rf[3 + j] + Rt[6 + i] * Rf[6 + j];
+        for (int i = 0; i < 9; ++i) m[MEM_PREV_EE_ROT + 9 * lane + i] = Rrel[i];
+      } else {
+        for (int i = 0; i < 3; ++i) {
+          m[MEM_PREV_TRUNK_REF + i] = T[9 + i];                      // prev_trunk_ref (:370)
+          r[REF_DEF_TRUNK_ORI + i] = eul[i];                         // default_trunk_ori (:363-364)
+          r[REF_INIT_TRUNK_POS + i] = T[9 + i];                      // initial_trunk_pos (:379)
+          r[REF_INIT_TRUNK_EUL + i] = eul[i];                        // initial_trunk_ori_euler (:381-383)
+        }
+        for (int i = 0; i < 9; ++i) m[MEM_OLD_TRUNK_ROT + i] = Rf[i];  // old_ref_trunk_rot_matrix (:371)
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// pin.integrate(model, q, v)  (jointVelocitiestoConfig, Robot_Wrapper4.py:440-441): one state per warp
+__global__ void __launch_bounds__(256) wbc_integrate_kernel(const DevModel* __restrict__ model, const double* __restrict__ q,
+                                                            const double* __restrict__ v, long long N, double scale,
+                                                            double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nq = model->nq, nv = model->nv;
+  for (long long s = wid; s < N; s += nw) {
+    const double* qs = q + s * nq;
+    const double* vs = v + s * nv;
+    double* o = out + s * nq;
+    if (lane == 0) {
+      double q7[7], v6[6], o7[7];
+      for (int i = 0; i < 7; ++i) q7[i] = qs[i];
+      for (int i = 0; i < 6; ++i) v6[i] = vs[i] * scale;
+      integrate_freeflyer(q7, v6, o7);
+      for (int i = 0; i < 7; ++i) o[i] = o7[i];
+    } else if (lane >= 6 && lane < nv) {
+      const int iq = model->col_q[lane];
+      o[iq] = qs[iq] + vs[lane] * scale;
+    }
+  }
+}
+
+// standalone batched QP: QP(A, b, lb, ub, C, Clb, Cub).solveQP()  (QP_Wrapper.py:10-53)
+struct QpParams {
+  long long N;
+  int nv, m, nC, max_iter;
+  const double *A, *b, *H, *g, *lb, *ub, *C, *Clb, *Cub;
+  double* x;
+  int* status;
+  int* iters;
+  unsigned long long* active_set;
+};
+
+__global__ void __launch_bounds__(256) wbc_qp_kernel(const __grid_constant__ QpParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int n = P.nv, LD = n | 1, nC = P.nC;
+  const int per_warp = 2 * n * LD + nC * LD + 3 * 32 + ((2 * n * LD + nC * LD) & 1);
+  double* ws = reinterpret_cast<double*>(smem_raw) + (size_t)warp * per_warp;
+  QpShared S;
+  S.M0 = ws;
+  S.J = ws + n * LD;
+  S.C = S.J + n * LD;
+  S.vx = S.C + nC * LD;
+  S.vd = S.vx + 32;
+  S.vg = S.vd + 32;
+  for (long long s = (long long)blockIdx.x * wpc + warp; s < P.N; s += (long long)gridDim.x * wpc) {
+    double gk = 0.0;
+    if (P.H) {
+      for (int i = lane; i < n * n; i += 32) S.M0[(i / n) * LD + (i % n)] = P.H[s * n * n + i];
+      if (lane < n) gk = P.g[s * n + lane];
+    } else {
+      // H = A^T A, g = -A^T b  (QP_Wrapper.py:17-18): row r of A staged in vx, lane k accumulates row k of H
+      for (int i = lane; i < n * LD; i += 32) S.M0[i] = 0.0;
+      __syncwarp();
+      const double* Ag = P.A + s * (long long)P.m * n;
+      const double* bg = P.b + s * (long long)P.m;
+      for (int r = 0; r < P.m; ++r) {
+        const double ark = (lane < n) ? Ag[r * n + lane] : 0.0;
+        S.vx[lane] = ark;
+        __syncwarp();
+        if (lane < n) {
+          double* Hrow = S.M0 + lane * LD;
+          for (int l = 0; l < n; ++l) Hrow[l] += ark * S.vx[l];
+          gk -= ark * bg[r];
+        }
+        __syncwarp();
+      }
+    }
+    if (nC > 0)
+      for (int i = lane; i < nC * n; i += 32) S.C[(i / n) * LD + (i % n)] = P.C[s * (long long)nC * n + i];
+    const double lbv = (lane < n) ? P.lb[s * n + lane] : 0.0, ubv = (lane < n) ? P.ub[s * n + lane] : 0.0;
+    const double clb = (lane < nC) ? P.Clb[s * nC + lane] : 0.0, cub = (lane < nC) ? P.Cub[s * nC + lane] : 0.0;
+    __syncwarp();
+    double x;
+    const QpResult res = warp_qp_solve<0>(S, n, LD, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
+    if (lane < n) P.x[s * n + lane] = x;
+    if (lane == 0) {
+      P.status[s] = res.status;
+      P.iters[s] = res.iters;
+      if (P.active_set) { P.active_set[2 * s] = res.act_box; P.active_set[2 * s + 1] = res.act_rows; }
+    }
+    __syncwarp();
+  }
+}
+
+// DFMA-saturating microkernel: 8 independent FMA chains per thread
+__global__ void __launch_bounds__(256) wbc_dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
+  memset(m, 0, sizeof(*m));
+  if (t->njoints < 2 || t->njoints > WBC_MAX_JOINTS) return fail(WBC_ERR_INVALID_ARG, "njoints out of range%s");
+  if (t->nv < 6 || t->nv > WBC_MAX_NV || t->nq != t->nv + 1) return fail(WBC_ERR_INVALID_ARG, "need 6 <= nv <= 32 and nq == nv + 1%s");
+  if (t->nframes < WBC_HOT_FRAMES || t->nframes > WBC_MAX_FRAMES) return fail(WBC_ERR_INVALID_ARG, "need 6..16 frame slots (5 EE + trunk first)%s");
+  if (t->jtype[1] != WBC_JT_FREEFLYER || t->parent[1] != 0) return fail(WBC_ERR_INVALID_ARG, "joint 1 must be the free-flyer root%s");
+  m->njoints = t->njoints; m->nq = t->nq; m->nv = t->nv; m->nframes = t->nframes;
+  int maxd = 0;
+  for (int j = 0; j < t->njoints; ++j) {
+    m->parent[j] = t->parent[j];
+    m->jtype[j] = t->jtype[j];
+    m->idx_q[j] = t->idx_q[j];
+    if (j > 0) {
+      if (t->parent[j] < 0 || t->parent[j] >= j) return fail(WBC_ERR_INVALID_ARG, "parents must precede children%s");
+      if (j > 1 && t->jtype[j] != WBC_JT_REVOLUTE && t->jtype[j] != WBC_JT_PRISMATIC)
+        return fail(WBC_ERR_UNSUPPORTED, "only revolute / prismatic joints below the free-flyer root%s");
+      m->depth[j] = m->depth[t->parent[j]] + 1;
+      if (m->depth[j] > maxd) maxd = m->depth[j];
+    }
+    memcpy(m->plR[j], t->placement_R[j], sizeof(double) * 9);
+    memcpy(m->plp[j], t->placement_p[j], sizeof(double) * 3);
+    memcpy(m->axis[j], t->axis[j], sizeof(double) * 3);
+    m->mass[j] = t->mass[j];
+    memcpy(m->com[j], t->com[j], sizeof(double) * 3);
+    m->total_mass += t->mass[j];
+  }
+  m->maxdepth = maxd;
+  for (int k = 0; k < WBC_MAX_NV; ++k) m->col_q[k] = -1;
+  for (int j = 1; j < t->njoints; ++j) {
+    const int iv = t->idx_v[j];
+    if (t->jtype[j] == WBC_JT_FREEFLYER) {
+      for (int e = 0; e < 3; ++e) {
+        m->col_joint[iv + e] = j; m->col_ang[iv + e] = 0; m->col_axis[iv + e][e] = 1.0;
+        m->col_joint[iv + 3 + e] = j; m->col_ang[iv + 3 + e] = 1; m->col_axis[iv + 3 + e][e] = 1.0;
+      }
+    } else {
+      m->col_joint[iv] = j;
+      m->col_ang[iv] = (t->jtype[j] == WBC_JT_REVOLUTE);
+      memcpy(m->col_axis[iv], t->axis[j], sizeof(double) * 3);
+      m->col_q[iv] = t->idx_q[j];
+    }
+  }
+  for (int j = 1; j < t->njoints; ++j) {
+    uint32_t mask = 0;
+    for (int a = j; a > 0; a = t->parent[a]) {
+      const int nvj = (t->jtype[a] == WBC_JT_FREEFLYER) ? 6 : 1;
+      for (int k = t->idx_v[a]; k < t->idx_v[a] + nvj; ++k) {
+        mask |= 1u << k;
+        m->sub_joints[k] |= 1u << j;           // column k moves joint j
+      }
+    }
+    m->joint_supp[j] = mask;
+  }
+  for (int f = 0; f < t->nframes; ++f) {
+    if (t->frame_parent[f] < 0 || t->frame_parent[f] >= t->njoints) return fail(WBC_ERR_INVALID_ARG, "frame parent out of range%s");
+    m->frame_parent[f] = t->frame_parent[f];
+    m->frame_supp[f] = m->joint_supp[t->frame_parent[f]];
+    memcpy(m->frR[f], t->frame_R[f], sizeof(double) * 9);
+    memcpy(m->frp[f], t->frame_p[f], sizeof(double) * 3);
+  }
+  memcpy(m->lower, t->lower, sizeof(double) * WBC_MAX_NQ);
+  memcpy(m->upper, t->upper, sizeof(double) * WBC_MAX_NQ);
+  memcpy(m->velocity, t->velocity, sizeof(double) * WBC_MAX_NV);
+  return WBC_OK;
+}
+
+static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15); }
+
+template <int NV, bool DBG>
+static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
+  const StepLayout L = step_layout(NV, P.nC);
+  const size_t per_warp = (size_t)L.total * sizeof(double);
+  int max_optin = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, model->device));
+  int warps = (int)(((size_t)max_optin - model_smem_bytes()) / per_warp);
+  if (warps > 12) warps = 12;
+  if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
+  const size_t smem = model_smem_bytes() + warps * per_warp;
+  auto kern = wbc_step_kernel<NV, DBG>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long need = (P.N + warps - 1) / warps;
+  int grid = (int)(need < model->sm_count ? need : model->sm_count);
+  if (grid < 1) grid = 1;
+  if (info) {
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
+    info[0] = model->sm_count; info[1] = warps * 32; info[2] = (int)smem; info[3] = fa.numRegs;
+    return WBC_OK;
+  }
+  if (P.N == 0) return WBC_OK;
+  kern<<<grid, warps * 32, smem, st>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return WBC_OK;
+}
+
+template <bool DBG>
+static int launch_step(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
+  switch (model->host.nv) {
+    case 25: return launch_step_t<25, DBG>(model, P, st, info);
+    case 26: return launch_step_t<26, DBG>(model, P, st, info);
+    case 18: return launch_step_t<18, DBG>(model, P, st, info);
+    default: return fail(WBC_ERR_UNSUPPORTED, "step kernel is instantiated for nv in {18, 25, 26}%s");
+  }
+}
+
+static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, StepParams* P) {
+  if (!model || !cfg || !io) return fail(WBC_ERR_INVALID_ARG, "null model / config / io%s");
+  if (cfg->joint_mode == WBC_JOINT_MANI || cfg->joint_mode == WBC_JOINT_HYBRID)
+    if (cfg->task_mask & WBC_TASK_JOINT) return fail(WBC_ERR_UNSUPPORTED, "joint-task modes MANI / HYBRID are not implemented yet%s");
+  if (cfg->n_extra_rows < 0 || cfg->n_extra_rows > WBC_MAX_EXTRA_ROWS) return fail(WBC_ERR_INVALID_ARG, "n_extra_rows out of range%s");
+  for (int e = 0; e < cfg->n_extra_rows; ++e)
+    if (cfg->extra_frame[e] < 0 || cfg->extra_frame[e] >= WBC_HOT_FRAMES) return fail(WBC_ERR_INVALID_ARG, "extra row frame must be a hot frame slot 0..5%s");
+  if (!(cfg->task_mask & 0x7f)) return fail(WBC_ERR_INVALID_ARG, "no task selected%s");
+  if (!io->q || !io->targets || !io->mem_in || !io->ref) return fail(WBC_ERR_INVALID_ARG, "q / targets / mem_in / ref are required%s");
+  if (!(io->dt > 0.0)) return fail(WBC_ERR_INVALID_ARG, "dt must be positive%s");
+  P->model = model->dev;
+  P->cfg = *cfg;
+  P->io = *io;
+  memset(&P->dbg, 0, sizeof(P->dbg));
+  P->nC = cfg_nc(*cfg);
+  P->m_rows = cfg_m(*cfg, model->host.nv);
+  P->flags = (int)io->flags;
+  if (P->nC > WBC_MAX_NC) return fail(WBC_ERR_UNSUPPORTED, "more than 32 constraint rows%s");
+  return WBC_OK;
+}
+
+extern "C" {
+
+int wbc_abi_version(void) { return WBC_ABI_VERSION; }
+const char* wbc_last_error(void) { return g_err; }
+
+int wbc_model_create(const WbcTreeTable* table, WbcModel** out_model) {
+  if (!table || !out_model) return fail(WBC_ERR_INVALID_ARG, "null argument%s");
+  WbcModel* m = new (std::nothrow) WbcModel;
+  if (!m) return fail(WBC_ERR_INVALID_ARG, "out of host memory%s");
+  int rc = build_dev_model(table, &m->host);
+  if (rc != WBC_OK) { delete m; return rc; }
+  cudaError_t e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
+  if (e == cudaSuccess) e = cudaMalloc(&m->dev, sizeof(DevModel));
+  if (e == cudaSuccess) e = cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete m;
+    return fail(WBC_ERR_CUDA, "wbc_model_create: %s (no CUDA device? there is no CPU fallback)", cudaGetErrorString(e));
+  }
+  *out_model = m;
+  return WBC_OK;
+}
+
+void wbc_model_destroy(WbcModel* model) {
+  if (!model) return;
+  cudaFree(model->dev);
+  delete model;
+}
+
+int wbc_config_rows(const WbcConfig* cfg, int32_t nv, int32_t* m_rows, int32_t* nc_rows) {
+  if (!cfg) return fail(WBC_ERR_INVALID_ARG, "null config%s");
+  if (m_rows) *m_rows = cfg_m(*cfg, nv);
+  if (nc_rows) *nc_rows = cfg_nc(*cfg);
+  return WBC_OK;
+}
+
+static int fk_common(const WbcModel* model, FkJacParams& P, void* stream) {
+  const int wpc = 8;
+  const size_t per_warp = (WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40) * sizeof(double);
+  const size_t smem = model_smem_bytes() + wpc * per_warp;
+  CUDA_TRY(cudaFuncSetAttribute(wbc_fk_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (P.N == 0) return WBC_OK;
+  long long need = (P.N + wpc - 1) / wpc;
+  const long long cap = (long long)model->sm_count * 4;
+  const int grid = (int)(need < cap ? need : cap);
+  wbc_fk_jac_kernel<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return WBC_OK;
+}
+
+int wbc_fk_jac(const WbcModel* model, const double* q, int64_t N, const int32_t* frame_slots, int32_t nsel,
+               int32_t ref_frame, double* out_oMf, double* out_J, void* stream) {
+  if (!model || !q || N < 0) return fail(WBC_ERR_INVALID_ARG, "null model / q or negative N%s");
+  if (nsel < 0 || nsel > WBC_MAX_FRAMES || (nsel > 0 && !frame_slots)) return fail(WBC_ERR_INVALID_ARG, "bad frame selection%s");
+  if (ref_frame < 0 || ref_frame > 2) return fail(WBC_ERR_INVALID_ARG, "ref_frame must be WORLD, LOCAL or LOCAL_WORLD_ALIGNED%s");
+  FkJacParams P;
+  memset(&P, 0, sizeof(P));
+  P.model = model->dev; P.q = q; P.N = N; P.nsel = nsel; P.rf = ref_frame;
+  for (int i = 0; i < nsel; ++i) {
+    if (frame_slots[i] < 0 || frame_slots[i] >= model->host.nframes) return fail(WBC_ERR_INVALID_ARG, "frame slot out of range%s");
+    P.slots[i] = frame_slots[i];
+  }
+  P.out_oMf = out_oMf; P.out_J = out_J;
+  return fk_common(model, P, stream);
+}
+
+int wbc_joint_jacobians(const WbcModel* model, const double* q, int64_t N, double* out_oMi, double* out_J, void* stream) {
+  if (!model || !q || N < 0) return fail(WBC_ERR_INVALID_ARG, "null model / q or negative N%s");
+  FkJacParams P;
+  memset(&P, 0, sizeof(P));
+  P.model = model->dev; P.q = q; P.N = N;
+  P.out_oMi = out_oMi; P.out_Jw = out_J;
+  return fk_common(model, P, stream);
+}
+
+int wbc_init_memory(const WbcModel* model, const double* q, int64_t N, double* mem_out, double* ref_out, void* stream) {
+  if (!model || !q || !mem_out || !ref_out || N < 0) return fail(WBC_ERR_INVALID_ARG, "null argument or negative N%s");
+  const int wpc = 8;
+  const size_t per_warp = (WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40) * sizeof(double);
+  const size_t smem = model_smem_bytes() + wpc * per_warp;
+  CUDA_TRY(cudaFuncSetAttribute(wbc_init_memory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (N == 0) return WBC_OK;
+  long long need = (N + wpc - 1) / wpc;
+  const long long cap = (long long)model->sm_count * 4;
+  wbc_init_memory_kernel<<<(int)(need < cap ? need : cap), wpc * 32, smem, (cudaStream_t)stream>>>(model->dev, q, N, mem_out, ref_out);
+  CUDA_TRY(cudaGetLastError());
+  return WBC_OK;
+}
+
+int wbc_integrate(const WbcModel* model, const double* q, const double* v, int64_t N, double scale, double* q_out,
+                  void* stream) {
+  if (!model || !q || !v || !q_out || N < 0) return fail(WBC_ERR_INVALID_ARG, "null argument or negative N%s");
+  if (N == 0) return WBC_OK;
+  long long need = (N + 7) / 8;
+  const long long cap = (long long)model->sm_count * 8;
+  wbc_integrate_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(model->dev, q, v, N, scale, q_out);
+  CUDA_TRY(cudaGetLastError());
+  return WBC_OK;
+}
+
+int wbc_assemble(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, int64_t N,
+                 const WbcAssembleOut* out, void* stream) {
+  StepParams P;
+  int rc = check_cfg(model, cfg, io, &P);
+  if (rc != WBC_OK) return rc;
+  if (!out || N < 0) return fail(WBC_ERR_INVALID_ARG, "null outputs or negative N%s");
+  P.dbg = *out;
+  P.N = N;
+  return launch_step<true>(model, P, (cudaStream_t)stream, nullptr);
+}
+
+int wbc_step(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, int64_t N, void* stream) {
+  StepParams P;
+  int rc = check_cfg(model, cfg, io, &P);
+  if (rc != WBC_OK) return rc;
+  if (N < 0 || !io->qdot || !io->status || !io->iters) return fail(WBC_ERR_INVALID_ARG, "qdot / status / iters are required%s");
+  P.N = N;
+  return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
+}
+
+int wbc_step_launch_info(const WbcModel* model, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* regs) {
+  if (!model) return fail(WBC_ERR_INVALID_ARG, "null model%s");
+  StepParams P;
+  memset(&P, 0, sizeof(P));
+  P.nC = 16;
+  P.N = 1 << 20;
+  int info[4] = {0, 0, 0, 0};
+  int rc = launch_step<false>(model, P, nullptr, info);
+  if (rc != WBC_OK) return rc;
+  if (grid) *grid = info[0];
+  if (block) *block = info[1];
+  if (smem_bytes) *smem_bytes = info[2];
+  if (regs) *regs = info[3];
+  return WBC_OK;
+}
+
+int wbc_qp_solve(int64_t N, int32_t nv, int32_t m, int32_t nC, const double* A, const double* b, const double* H,
+                 const double* g, const double* lb, const double* ub, const double* C, const double* Clb,
+                 const double* Cub, int32_t max_iter, double* x, int32_t* status, int32_t* iters,
+                 uint64_t* active_set, void* stream) {
+  if (N < 0 || nv < 1 || nv > WBC_MAX_NV) return fail(WBC_ERR_INVALID_ARG, "need N >= 0 and 1 <= nv <= 32%s");
+  if (nC < 0 || nC > WBC_MAX_NC) return fail(WBC_ERR_UNSUPPORTED, "need 0 <= nC <= 32%s");
+  const bool haveA = A && b, haveH = H && g;
+  if (haveA == haveH) return fail(WBC_ERR_INVALID_ARG, "give exactly one of (A, b) or (H, g)%s");
+  if (haveA && m < 1) return fail(WBC_ERR_INVALID_ARG, "A needs m >= 1 rows%s");
+  if (!lb || !ub || !x || !status || !iters) return fail(WBC_ERR_INVALID_ARG, "lb / ub / x / status / iters are required%s");
+  if (nC > 0 && (!C || !Clb || !Cub)) return fail(WBC_ERR_INVALID_ARG, "C / Clb / Cub are required when nC > 0%s");
+  if (N == 0) return WBC_OK;
+  QpParams P;
+  P.N = N; P.nv = nv; P.m = m; P.nC = nC; P.max_iter = max_iter > 0 ? max_iter : 200;
+  P.A = haveA ? A : nullptr; P.b = haveA ? b : nullptr; P.H = haveH ? H : nullptr; P.g = haveH ? g : nullptr;
+  P.lb = lb; P.ub = ub; P.C = C; P.Clb = Clb; P.Cub = Cub;
+  P.x = x; P.status = status; P.iters = iters; P.active_set = (unsigned long long*)active_set;
+  const int LD = nv | 1;
+  const int per_warp = 2 * nv * LD + nC * LD + 96 + ((2 * nv * LD + nC * LD) & 1);
+  const int wpc = 8;
+  const size_t smem = (size_t)wpc * per_warp * sizeof(double);
+  CUDA_TRY(cudaFuncSetAttribute(wbc_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long need = (N + wpc - 1) / wpc;
+  const long long cap = (long long)sms * 2;
+  wbc_qp_kernel<<<(int)(need < cap ? need : cap), wpc * 32, smem, (cudaStream_t)stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return WBC_OK;
+}
+
+int wbc_measure_fp64_peak(double* flops_per_s, void* stream) {
+  if (!flops_per_s) return fail(WBC_ERR_INVALID_ARG, "null output%s");
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+  double* buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  wbc_dfma_kernel<<<blocks, threads, 0, st>>>(buf, 1024);           // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    wbc_dfma_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *flops_per_s = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3);
+  return WBC_OK;
+}
+
+}  // extern "C"

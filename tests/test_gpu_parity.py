@@ -1,0 +1,198 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): FK poses / frame Jacobians 1e-10 abs, QP solutions 1e-6 with
+an identical active set.  All arithmetic is float64.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+FK_TOL = 1e-10
+QP_TOL = 1e-6
+
+
+def _robot(name, N, tasks, cons, joint=True):
+    import wbc_b200
+    r = wbc_b200.RobotModel(name, batch=N, device="cuda:0")
+    r.setTasks(Trunk=tasks["Trunk"], FR=tasks["FR"], FL=tasks["FL"], RR=tasks["RR"], RL=tasks["RL"], Grip=tasks["Grip"],
+               Joint=joint)
+    r.setConstraints(**cons)
+    return r
+
+
+P1_TASKS = dict(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True)
+P2_TASKS = dict(Trunk=False, FR=False, FL=False, RR=False, RL=False, Grip=True)
+NO_CONS = dict(CoM=False, Trunk=False, FR=False, FL=False, RR=False, RL=False, Grip=False)
+P2_CONS = dict(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+
+
+def _load(robot, N, seed, sigma):
+    from wbc_b200 import synthetic
+    q = synthetic.sample_configurations(robot.robot_model, N, seed)
+    noise = synthetic.sample_noise(N, seed, sigma)
+    targets = synthetic.load_batch(robot, q, noise)
+    return q, targets
+
+
+@pytest.mark.parametrize("name", ["a1_wx200", "a1_px100_pin_ver"])
+def test_fk_and_frame_jacobians_match_oracle(name):
+    import wbc_b200
+    from wbc_b200 import synthetic
+    N = 256
+    robot = wbc_b200.RobotModel(name, batch=N, device="cuda:0")
+    q = synthetic.sample_configurations(robot.robot_model, N, 11)
+    q[N // 2:, 3:7] = np.random.default_rng(5).normal(size=(N - N // 2, 4))     # uniform SO(3) half
+    q[N // 2:, 3:7] /= np.linalg.norm(q[N // 2:, 3:7], axis=1, keepdims=True)
+    robot.updateState(torch.as_tensor(q, device="cuda:0"), feedback=False)
+    model = H.oracle_model(name)
+    data = model.createData()
+    got = {rf: robot.frameJacobians(rf) for rf in (0, 1, 2)}
+    oMi = robot._oMi.cpu().numpy()
+    Jw = robot.J.cpu().numpy()
+    frames = robot.end_effector_index_list_frame + [robot.trunk_frame_index]
+    worst = 0.0
+    for s in range(0, N, 3):
+        H.opin.forwardKinematics(model, data, q[s])
+        H.opin.computeJointJacobians(model, data, q[s])
+        H.opin.updateFramePlacements(model, data)
+        worst = max(worst, np.abs(Jw[s] - data.J).max())
+        for j in range(1, model.njoints):
+            ref = np.concatenate([data.oMi[j].rotation.reshape(-1), data.oMi[j].translation])
+            worst = max(worst, np.abs(oMi[s, j] - ref).max())
+        for rf in (0, 1, 2):
+            oMf, J = got[rf]
+            for k, fid in enumerate(frames):
+                Jr = H.opin.getFrameJacobian(model, data, fid, rf)
+                worst = max(worst, np.abs(J[s, k].cpu().numpy() - Jr).max())
+                ref = np.concatenate([data.oMf[fid].rotation.reshape(-1), data.oMf[fid].translation])
+                worst = max(worst, np.abs(oMf[s, k].cpu().numpy() - ref).max())
+    assert worst < FK_TOL, worst
+
+
+def test_golden_jacobians_neutral_wx200():
+    """Reference's recorded Pinocchio output tests_NOT_FOR_USE/Jacobians.py:1-24 through the CUDA path."""
+    import wbc_b200
+    g = H.golden("jacobians_neutral_wx200.json")
+    robot = wbc_b200.RobotModel("a1_wx200", batch=1, device="cuda:0")
+    Jw = robot.J[0].cpu().numpy()                       # constructor leaves the model at pin.neutral
+    t = robot.robot_model
+    for key, jid in (("joint19", 19), ("joint1", 1), ("joint4", 4)):
+        G = np.array(g[key])
+        mask = np.array([(t.support_mask(jid) >> k) & 1 for k in range(t.nv)], dtype=float)
+        Jj = Jw * mask
+        if key == "joint19":
+            typo = g["known_typo"]
+            assert G[typo["row"], typo["col"]] == typo["recorded"]
+            G[typo["row"], typo["col"]] = typo["geometry"]
+        assert np.abs(Jj - G).max() < 5e-7, key        # the dump is printed with 6 decimals
+
+
+@pytest.mark.parametrize("name,tasks,cons,joint,sigma", [
+    ("a1_px100_pin_ver", P1_TASKS, NO_CONS, True, 5e-3),      # P1 bootstrap pattern: bounds only
+    ("a1_px100_pin_ver", P2_TASKS, P2_CONS, "PREV", 5e-4),    # P2 sim3 tick pattern
+    ("a1_wx200", P1_TASKS, P2_CONS, True, 5e-3),              # P3 full stack + constraints (stress sigma)
+    ("a1_wx200", P1_TASKS, P2_CONS, True, 5e-4),              # P3 nominal sigma
+])
+def test_assembly_and_qp_match_oracle(name, tasks, cons, joint, sigma):
+    N = 96
+    robot = _robot(name, N, tasks, cons, joint)
+    q, targets = _load(robot, N, 20260002, sigma)
+    mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+    asm = robot.assemble(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18])
+    imu = torch.as_tensor(q[:, 3:7], device="cuda:0")
+    qdot = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], imu_quat=imu, advance=True).cpu().numpy()
+    ref = H.oracle_step_batch(name, robot, q, targets.cpu().numpy(), mem0.cpu().numpy(), ref0.cpu().numpy(),
+                              imu=q[:, 3:7], tail=True)
+    for k in ("A", "lb", "ub", "C"):
+        assert np.abs(asm[k].cpu().numpy() - ref[k]).max() < FK_TOL, k
+    for k in ("b", "Clb", "Cub", "g"):          # these carry 1/dt = 500: scale the tolerance with the magnitude
+        a, r = asm[k].cpu().numpy(), ref[k]
+        assert np.abs(a - r).max() < 1e-9 * max(1.0, np.abs(r).max()), k
+    assert np.abs(asm["H"].cpu().numpy() - ref["H"]).max() < 1e-10
+    status = robot.last_status.cpu().numpy()
+    assert (status == 0).all() and (ref["status"] == 0).all()
+    assert np.abs(qdot - ref["qdot"]).max() < QP_TOL
+    # identical active set and identical pivoting path
+    act = robot.last_active_set.cpu().numpy().astype(np.uint64)
+    nv = robot.n_velocity_dimensions
+    for s in range(N):
+        wb, wr = H.act_to_bits(ref["act"][s], nv)
+        assert int(act[s, 0]) == wb and int(act[s, 1]) == wr, s
+    assert (robot.last_iters.cpu().numpy() == ref["iters"]).all()
+    # task memory and next configuration (integrate + base estimate)
+    assert np.abs(robot._mem.cpu().numpy() - ref["mem_out"]).max() < 1e-12
+    assert np.abs(robot.current_joint_config.cpu().numpy() - ref["q_next"]).max() < 1e-8
+
+
+def test_qp_kat_and_random_problems():
+    """QP drop-in: the reference's only QP example (tests_NOT_FOR_USE/qp_tests.py) + random dense problems."""
+    import wbc_b200
+    from oracle.qp_wrapper import solve_qp
+    kat = H.golden("qp_kat.json")
+    P, qv = np.array(kat["P"]), np.array(kat["q"])
+    L = np.linalg.cholesky(P)
+    A = L.T                                           # A^T A = P
+    b = -np.linalg.solve(L, qv)                        # -A^T b = q
+    big = 1e30
+    Cm = np.vstack([np.array(kat["G"]), np.array(kat["A"])])
+    Clb = np.concatenate([-big * np.ones(3), np.array(kat["b"])])
+    Cub = np.concatenate([np.array(kat["h"]), np.array(kat["b"])])
+    qp = wbc_b200.QP(A, b, -big * np.ones(3), big * np.ones(3), Cm.T, Clb, Cub, n_of_velocity_dimensions=3)
+    x = qp.solveQP().cpu().numpy()
+    assert np.abs(x - np.array(kat["x"])).max() < 1e-9
+    assert int(qp.status[0]) == 0
+
+    rng = np.random.default_rng(3)
+    N, n, m, nC = 128, 26, 62, 16
+    A = rng.normal(size=(N, m, n)); A[:, 36:, :] = 0
+    A[:, 36:, :] = np.eye(n)[None] * (0.05 / 26)
+    b = rng.normal(size=(N, m)) * 3
+    lb = -rng.uniform(0, 2, (N, n)); ub = rng.uniform(0, 2, (N, n)); lb[:, 23:] = 0; ub[:, 23:] = 0
+    Cm = rng.normal(size=(N, nC, n)); Clb = -rng.uniform(0, 1, (N, nC)); Cub = rng.uniform(0, 1, (N, nC))
+    Clb[:, 4:] = 0; Cub[:, 4:] = 0
+    qp = wbc_b200.QP(A, b, lb, ub, np.transpose(Cm, (0, 2, 1)), Clb, Cub, n_of_velocity_dimensions=n)
+    x = qp.solveQP().cpu().numpy()
+    assert (qp.status.cpu().numpy() == 0).all()
+    for s in range(N):
+        Hs, gs = A[s].T @ A[s], -A[s].T @ b[s]
+        r = solve_qp(Hs, gs, lb[s], ub[s], Cm[s], Clb[s], Cub[s])
+        assert np.abs(x[s] - r["x"]).max() < QP_TOL
+        k = H.kkt_residuals(Hs, gs, lb[s], ub[s], Cm[s], Clb[s], Cub[s], x[s])
+        assert max(k.values()) < 1e-7, (s, k)
+        assert int(qp.iters[s]) == r["iters"]
+    # bounds-only path (QProblemB)
+    qp2 = wbc_b200.QP(A, b, lb, ub, n_of_velocity_dimensions=n)
+    x2 = qp2.solveQP().cpu().numpy()
+    for s in range(0, N, 8):
+        r = solve_qp(A[s].T @ A[s], -A[s].T @ b[s], lb[s], ub[s])
+        assert np.abs(x2[s] - r["x"]).max() < QP_TOL
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 size (PX100, 4096 states): size-independent properties of every solution."""
+    N = 4096
+    robot = _robot("a1_px100_pin_ver", N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260001, 5e-3)
+    asm = robot.assemble(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], want=("C", "Clb", "Cub", "lb", "ub", "H", "g"))
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=False)
+    assert (robot.last_status == 0).all()
+    Cx = torch.einsum("nrk,nk->nr", asm["C"], x)
+    assert (Cx >= asm["Clb"] - 1e-8).all() and (Cx <= asm["Cub"] + 1e-8).all()
+    assert (x >= asm["lb"] - 1e-9).all() and (x <= asm["ub"] + 1e-9).all()
+    # foot rows are equalities: J_foot qdot = 0
+    assert Cx[:, 4:].abs().max() < 1e-8
+    # stationarity on the free subspace: the gradient lies in the span of the active normals
+    grad = torch.einsum("nij,nj->ni", asm["H"], x) + asm["g"]
+    act = robot.last_active_set.cpu().numpy().astype(np.uint64)
+    Cn, gn, xn = asm["C"].cpu().numpy(), grad.cpu().numpy(), x.cpu().numpy()
+    nv = robot.n_velocity_dimensions
+    for s in range(0, N, 64):
+        normals = [np.eye(nv)[k] for k in range(nv) if (int(act[s, 0]) >> (2 * k)) & 3]
+        normals += [Cn[s, r] for r in range(Cn.shape[1]) if (int(act[s, 1]) >> (2 * r)) & 3]
+        Nm = np.array(normals).T
+        lam, *_ = np.linalg.lstsq(Nm, gn[s], rcond=None)
+        assert np.abs(Nm @ lam - gn[s]).max() < 1e-7, s
