@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- WBC steps/s of the fused B200 hot path (FK + Jacobians + task stack + bounds + constraints + QP).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU loop (oracle port) on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic states.  Default workload:
+A1+WX200, full step P3 (m = 62 task rows, nC = 16 constraint rows), 131072 states per GPU -- BASELINE.json
+configs[3] (the 1M-state sweep) sharded 8 ways, weak scaling: at --gpus 8 the job is exactly the 1M-state sweep.
+Inputs per GPU (q, targets, memory, references: 1128 B/state = 148 MB) exceed the 126 MB L2, so every timed
+step streams its inputs from HBM.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "wbc_steps_per_s"
+UNIT = "steps/s"
+
+
+def algorithmic_flops(nv, njoints, m, nC, kbar, rot_support_cols):
+    """SURVEY.md 8d per-state work (dense symmetric-half A^T A regardless of how the kernel exploits sparsity)."""
+    f_fkj = 63 * (njoints - 2) + 24 * nv + 12 * rot_support_cols + 700
+    f_asm = m * nv * (nv + 1) + 2 * m * nv
+    f_qp = nv ** 3 / 3 + 2 * nv ** 2 + kbar * (4 * nv ** 2 + 2 * nv * nC)
+    return f_fkj, f_asm, f_qp
+
+
+def algorithmic_bytes(nq, nv):
+    """read q + targets (18) + memory (72) + references (24) doubles; write qdot + status + iters."""
+    return 8 * nq + 8 * 18 + 8 * 72 + 8 * 24 + 8 * nv + 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU side: the oracle port timed on host cores (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    name, q, targets, mem, ref, dt = args
+    try:                                   # one BLAS thread per worker process: the pool already uses every core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from tests import helpers as H
+    rm = H.make_oracle(name, dt=dt)
+    rm.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
+    rm.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+    t0 = time.perf_counter()
+    iters = 0
+    for s in range(q.shape[0]):
+        r = H.oracle_step_one(rm, q[s], targets[s], mem[s], ref[s], solve=True, tail=False)
+        iters += r["iters"]
+    return time.perf_counter() - t0, iters
+
+
+def cpu_inputs(name, n, seed, sigma):
+    """Same synthetic distribution as the GPU run, FK for the targets evaluated by the oracle (CPU only)."""
+    from tests import helpers as H
+    from wbc_b200 import synthetic
+    from wbc_b200.tree_table import TreeTable
+    from scipy.spatial.transform import Rotation as R
+    table = TreeTable.load(name)
+    q = synthetic.sample_configurations(table, n, seed)
+    noise = synthetic.sample_noise(n, seed, sigma)
+    rm = H.make_oracle(name)
+    targets, mem, ref = np.zeros((n, 18)), np.zeros((n, 72)), np.zeros((n, 24))
+    for s in range(n):
+        rm.current_joint_config = q[s].copy()
+        rm.updateState(q[s], feedback=False)
+        rm.initialiseWBC(q[s, 3:7])
+        d = rm.robot_data
+        fr = rm.end_effector_index_list_frame + [rm.trunk_frame_index]
+        pos = np.concatenate([d.oMf[f].translation for f in fr])
+        targets[s] = pos + noise[s]
+        mem[s] = H.get_oracle_mem(rm)
+        mem[s, 15:60] = np.concatenate([d.oMf[f].rotation.reshape(-1) for f in fr[:5]])
+        mem[s, 63:72] = d.oMf[fr[5]].rotation.reshape(-1)
+        ref[s] = np.concatenate([np.concatenate([e.reshape(3) for e in rm.default_EE_ori_list]),
+                                 rm.default_trunk_ori.reshape(3), rm.initial_trunk_pos.reshape(3),
+                                 rm.initial_trunk_ori_euler.reshape(3)])
+    return q, targets, mem, ref
+
+
+def time_cpu_loop(name, n_states, seed, sigma, dt, cores):
+    """Oracle per-state loop under multiprocessing.Pool(cores) over contiguous chunks.  Returns steps/s etc."""
+    import multiprocessing as mp
+    q, targets, mem, ref = cpu_inputs(name, n_states, seed, sigma)
+    chunks = np.array_split(np.arange(n_states), cores)
+    jobs = [(name, q[c], targets[c], mem[c], ref[c], dt) for c in chunks if len(c)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with ctx.Pool(len(jobs)) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    return {"steps_per_s": n_states / busy, "wall_s": wall, "busy_s": busy, "kbar": sum(r[1] for r in res) / n_states}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0))
+    per_step = max(cores * 8, 16)
+    for _ in range(args.warmup):
+        time_cpu_loop(args.robot, max(cores, 4), args.seed, args.sigma, args.dt, cores)
+    t_busy, n_done, kb = 0.0, 0, 0.0
+    for k in range(args.steps):
+        r = time_cpu_loop(args.robot, per_step, args.seed + k, args.sigma, args.dt, cores)
+        t_busy += r["busy_s"]; n_done += per_step; kb += r["kbar"]
+    value = n_done / t_busy
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_busy / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, per_gpu_states=per_step),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} states per step x {args.steps} steps, oracle (NumPy/SciPy restatement of "
+                                   f"Robot_Wrapper4 + QP_Wrapper; Pinocchio/qpOASES not installable) under "
+                                   f"multiprocessing.Pool({cores})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_qp_iterations": kb / args.steps,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, per_gpu_states):
+    return {"workload": f"A1+{'WX200' if 'wx200' in args.robot else 'PX100'} full WBC step P3: FK + 6 frame Jacobians + "
+                        f"task stack (FR,FL,RR,RL,GRIP,Trunk,Joint) + velocity-damper bounds + 16 constraint rows + QP",
+            "robot": args.robot, "states_per_gpu": per_gpu_states, "sigma": args.sigma, "dt": args.dt,
+            "baseline_config": "configs[3] (1M-state sweep) sharded 8-way: 131072 states/GPU, weak scaling",
+            "l2": "inputs per GPU (1128 B/state) exceed the 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import wbc_b200
+    from wbc_b200 import synthetic, _cabi as cabi
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_local = args.states
+    n_global = n_local * world
+    robot = wbc_b200.RobotModel(args.robot, batch=n_local, device=dev, dt=args.dt)
+    robot.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
+    robot.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+    table = robot.robot_model
+    # global arrays, then this rank's contiguous shard (results independent of the rank count)
+    qg = synthetic.sample_configurations(table, n_global, args.seed)
+    ng = synthetic.sample_noise(n_global, args.seed, args.sigma)
+    lo, hi = rank * n_local, (rank + 1) * n_local
+    targets = synthetic.load_batch(robot, qg[lo:hi], ng[lo:hi])
+    del qg, ng
+    ee_t, tr_t = targets[:, :15].reshape(n_local, 5, 3), targets[:, 15:18]
+    robot._pack_targets(ee_t, tr_t)
+    mem0 = robot._mem.clone()
+
+    def one_step():
+        robot.step(ee_t, tr_t, advance=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        evs[k][0].record()
+        one_step()
+        evs[k][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    per_step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = evs[0][0].elapsed_time(evs[-1][1])
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = n_global * args.steps / (total_ms_max * 1e-3)
+    status_ok = bool((robot.last_status == 0).all().item())
+    kbar = float(robot.last_iters.double().mean().item())
+    assert torch.equal(robot._mem, mem0), "advance=False must leave the task memory untouched"
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the public API -------------------
+    pin = dict(pin_memory=True)
+    host_in = {"q": robot.current_joint_config.cpu().pin_memory(), "targets": targets.cpu().pin_memory(),
+               "mem": robot._mem.cpu().pin_memory(), "ref": robot._ref.cpu().pin_memory()}
+    host_out = {"qdot": torch.empty(n_local, table.nv, dtype=torch.float64, **pin),
+                "status": torch.empty(n_local, dtype=torch.int32, **pin),
+                "iters": torch.empty(n_local, dtype=torch.int32, **pin)}
+    for _ in range(3):
+        h2d, d2h = robot.step_host(host_in, host_out)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e2e_steps):
+        robot.step_host(host_in, host_out)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_global * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_ok = bool((host_out["status"] == 0).all().item())
+
+    # ---- verification gather (off the timed path): NCCL all_gather of solutions / status -------------
+    verified = status_ok and e2e_ok
+    checksum = float(robot.qdot.double().abs().sum().item())
+    if world > 1:
+        gathered = torch.empty(world * n_local, table.nv, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, robot.qdot.contiguous())
+        st = torch.empty(world * n_local, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(st, robot.last_status.contiguous())
+        verified = verified and bool((st == 0).all().item()) and bool(torch.isfinite(gathered).all().item())
+        checksum = float(gathered.abs().sum().item())
+
+    if rank == 0:
+        # ---- FP64 roofline denominator: measured DFMA peak (MEASURED_PEAKS.json has none) ---------------
+        peak = C.c_double()
+        cabi.check(cabi.load().wbc_measure_fp64_peak(C.byref(peak), None))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        m_rows, nC = 36 + table.nv, 16
+        rot_cols = 4 * 6 + (3 + 5) + 3
+        f_fkj, f_asm, f_qp = algorithmic_flops(table.nv, table.njoints, m_rows, nC, kbar, rot_cols)
+        f_step = f_fkj + f_asm + f_qp
+        kern_s = (total_ms / args.steps) * 1e-3            # one kernel per step: average launch duration (CUDA events)
+        ach_tflops = f_step * n_local / kern_s / 1e12
+        bytes_state = algorithmic_bytes(table.nq, table.nv)
+        info = robot.launch_info()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_local),
+            "p50_step_us": float(np.median(per_step_ms) * 1e3),
+            "ns_per_state": 1e6 * total_ms_max / args.steps / n_global * world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "RobotModel.step_host -> wbc_step (C ABI), pinned host buffers"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64_fma", "achieved": ach_tflops, "peak": peak.value / 1e12, "unit": "TFLOP/s",
+                         "frac": ach_tflops / (peak.value / 1e12), "traffic": None,
+                         "peak_source": "measured in this run: DFMA-saturating microkernel (wbc_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "flops_per_state": {"fk_jac_targets": f_fkj, "AtA_sym_dense": f_asm, "qp": f_qp, "total": f_step},
+                         "note": "algorithmic flops per SURVEY 8d (dense symmetric A^T A); the kernel skips structural zeros"},
+            "roofline_hbm": {"bound": "hbm", "achieved": bytes_state * n_local / kern_s / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": bytes_state * n_local / kern_s / 1e9 / hbm_peak,
+                             "bytes_per_state": bytes_state,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
+            "mean_qp_iterations": kbar, "verified": verified, "checksum_abs_qdot": checksum,
+            "launch": info, "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = len(os.sched_getaffinity(0))
+            n_cpu = max(cores * 48, 64)
+            r = time_cpu_loop(args.robot, n_cpu, args.seed, args.sigma, args.dt, cores)
+            line["cpu_baseline"] = {"value": r["steps_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {n_cpu} states of the same synthetic distribution, oracle per-state "
+                                              f"loop (NumPy/SciPy restatement; Pinocchio/qpOASES not installable) under "
+                                              f"multiprocessing.Pool({cores}), wall {r['wall_s']:.1f} s",
+                                    "mean_qp_iterations": r["kbar"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--robot", default="a1_wx200")
+    ap.add_argument("--states", type=int, default=131072, help="states per GPU")
+    ap.add_argument("--sigma", type=float, default=5e-4)
+    ap.add_argument("--dt", type=float, default=0.002)
+    ap.add_argument("--seed", type=int, default=20260003)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

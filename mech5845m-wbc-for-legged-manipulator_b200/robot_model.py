@@ -557,6 +557,29 @@ class RobotModel:
             self.current_joint_config = q_next
         return self.qdot
 
+    def step_host(self, host_in, host_out):
+        """The fused tick with HOST buffers (what a caller holding NumPy arrays pays end to end).
+
+        ``host_in``: dict of pinned float64 CPU tensors q [N, nq], targets [N, 18], mem [N, 72], ref [N, 24];
+        ``host_out``: dict of pinned CPU tensors qdot [N, nv], status [N] (int32), iters [N] (int32).
+        Copies host -> device, launches the fused kernel, copies the results back, all on the current stream.
+        Returns (h2d_bytes, d2h_bytes).
+        """
+        self.current_joint_config.copy_(host_in["q"], non_blocking=True)
+        self._targets.copy_(host_in["targets"], non_blocking=True)
+        self._mem.copy_(host_in["mem"], non_blocking=True)
+        self._ref.copy_(host_in["ref"], non_blocking=True)
+        cfg = self._config()
+        io = self._io(targets=self._targets, qdot=self.qdot, status=self.last_status, iters=self.last_iters)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.wbc_step(self._model, C.byref(cfg), C.byref(io), self.N, _stream_ptr()))
+        host_out["qdot"].copy_(self.qdot, non_blocking=True)
+        host_out["status"].copy_(self.last_status, non_blocking=True)
+        host_out["iters"].copy_(self.last_iters, non_blocking=True)
+        h2d = sum(host_in[k].numel() * 8 for k in ("q", "targets", "mem", "ref"))
+        d2h = host_out["qdot"].numel() * 8 + host_out["status"].numel() * 4 + host_out["iters"].numel() * 4
+        return h2d, d2h
+
     def runWBC(self, base_config, target_cartesian_pos_EE=None, target_cartesian_pos_trunk=None):
         self.step(target_cartesian_pos_EE, target_cartesian_pos_trunk, imu_quat=base_config, advance=True)
         self.firstQP = False
