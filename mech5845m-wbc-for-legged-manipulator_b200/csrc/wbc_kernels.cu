@@ -49,8 +49,12 @@ __global__ void __launch_bounds__(384, 1) wbc_step_kernel(const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
-  for (long long s = (long long)blockIdx.x * wpc + warp; s < P.N; s += (long long)gridDim.x * wpc) {
-    warp_wbc_step<NV, DEBUG_OUT>(P, Ms, ws, L, s);
+  for (long long base = (long long)blockIdx.x * wpc; base < P.N; base += (long long)gridDim.x * wpc) {
+    long long s = base + warp;
+    const bool valid = s < P.N;          // padding warps shadow the last state so that block barriers stay uniform
+    if (!valid) s = P.N - 1;
+    if (DEBUG_OUT && !valid) continue;
+    warp_wbc_step<NV, DEBUG_OUT>(P, Ms, ws, L, s, valid);
     __syncwarp();
   }
 }
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(256) wbc_qp_kernel(const __grid_constant__ QpP
     const double clb = (lane < nC) ? P.Clb[s * nC + lane] : 0.0, cub = (lane < nC) ? P.Cub[s * nC + lane] : 0.0;
     __syncwarp();
     double x;
-    const QpResult res = warp_qp_solve<0>(S, n, LD, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
+    const QpResult res = warp_qp_solve_rt(S, n, LD, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
     if (lane < n) P.x[s * n + lane] = x;
     if (lane == 0) {
       P.status[s] = res.status;

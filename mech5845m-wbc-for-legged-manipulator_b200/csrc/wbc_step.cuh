@@ -130,7 +130,7 @@ __device__ __forceinline__ void integrate_freeflyer(const double* q, const doubl
 
 // calcTargetVelEE3 (Robot_Wrapper4.py:1052-1157): lane i in 0..4.  Writes b (6) and updates the staged memory.
 __device__ __forceinline__ void ee_task_target(const WbcConfig& cfg, int i, const double* __restrict__ oMf,
-                                               double* __restrict__ io, double dt, double* b) {
+                                               double* __restrict__ io, double inv_dt, double* b) {
   const double* target = io + WBC_IO_TARGETS + 3 * i;
   double* prev = io + WBC_IO_MEM + MEM_PREV_EE_POS + 3 * i;
   double* prevR = io + WBC_IO_MEM + MEM_PREV_EE_ROT + 9 * i;
@@ -138,8 +138,8 @@ __device__ __forceinline__ void ee_task_target(const WbcConfig& cfg, int i, cons
   double ref_vel[3], err[3], ge[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    ref_vel[k] = (target[k] - prev[k]) / dt;
-    err[k] = (target[k] - fk[k]) / dt;
+    ref_vel[k] = (target[k] - prev[k]) * inv_dt;
+    err[k] = (target[k] - fk[k]) * inv_dt;
   }
   mat3_vec(cfg.ee_gain_pos[i], err, ge);
   double qref[4], Rref[9];
@@ -147,7 +147,7 @@ __device__ __forceinline__ void ee_task_target(const WbcConfig& cfg, int i, cons
   scipy_matrix_from_quat(qref, Rref);
   double dR[9], sk[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) dR[k] = (Rref[k] - prevR[k]) / dt;
+  for (int k = 0; k < 9; ++k) dR[k] = (Rref[k] - prevR[k]) * inv_dt;
   mat3_mul_bt(dR, Rref, sk);                                   // (dR/dt) * Rref^T   (:1125)
   const double wgt = cfg.cart_task_weight[i];
   b[0] = (ref_vel[0] + ge[0]) * wgt;
@@ -164,7 +164,7 @@ __device__ __forceinline__ void ee_task_target(const WbcConfig& cfg, int i, cons
 
 // calcTargetVelTrunk2 (Robot_Wrapper4.py:948-1015): one lane.
 __device__ __forceinline__ void trunk_task_target(const WbcConfig& cfg, const double* __restrict__ oMf,
-                                                  const double* fkq, double* __restrict__ io, double dt, double* b) {
+                                                  const double* fkq, double* __restrict__ io, double inv_dt, double* b) {
   const double* target = io + WBC_IO_TARGETS + 15;
   double* prev = io + WBC_IO_MEM + MEM_PREV_TRUNK_REF;
   double* oldR = io + WBC_IO_MEM + MEM_OLD_TRUNK_ROT;
@@ -172,8 +172,8 @@ __device__ __forceinline__ void trunk_task_target(const WbcConfig& cfg, const do
   double ref_vel[3], err[3], ge[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    ref_vel[k] = (target[k] - prev[k]) / dt;
-    err[k] = (target[k] - fk[k]) / dt;
+    ref_vel[k] = (target[k] - prev[k]) * inv_dt;
+    err[k] = (target[k] - fk[k]) * inv_dt;
   }
   mat3_vec(cfg.trunk_gain_pos, err, ge);
   double r[4], Rref[9];
@@ -186,7 +186,7 @@ __device__ __forceinline__ void trunk_task_target(const WbcConfig& cfg, const do
   qe[2] = (f[0] * r[1]) - (f[1] * r[0]);                       // :976 -- the w*z terms cancel exactly
   double dR[9], sk[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) dR[k] = (Rref[k] - oldR[k]) / dt;
+  for (int k = 0; k < 9; ++k) dR[k] = (Rref[k] - oldR[k]) * inv_dt;
   mat3_mul(dR, Rref, sk);                                      // (dR/dt) * Rref, NOT transposed (:984)
   const double wgt = cfg.cart_task_weight[5];
   b[0] = (ref_vel[0] + ge[0]) * wgt;
@@ -233,15 +233,28 @@ __device__ __forceinline__ void damper_bounds(const DevModel* __restrict__ M, co
 }
 
 // One WBC tick for the state `sidx`, executed by one warp.  ws: this warp's shared workspace.
+// The warps of a CTA are re-aligned with a block barrier at the phase boundaries (PHASE_SYNC): the tick is
+// ~10^4 mostly straight-line instructions, far more than the instruction cache holds, so warps that drift apart
+// each stream the whole code through the cache on their own (ncu: 50 % of stall samples were `no_instruction`);
+// in step, one fetch feeds all warps.  `valid` == false: a padding warp that shadows the last state, no writes.
+template <bool ON>
+__device__ __forceinline__ void phase_sync() {
+  if (ON) __syncthreads();
+  else __syncwarp();
+}
+
 template <int NV, bool DEBUG_OUT>
 __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevModel* __restrict__ M,
-                                              double* __restrict__ ws, const StepLayout L, long long sidx) {
+                                              double* __restrict__ ws, const StepLayout L, long long sidx,
+                                              const bool valid) {
+  constexpr bool PS = !DEBUG_OUT;
   constexpr int LD = NV | 1;
   constexpr int LDA = NV + (NV & 1);
   const int lane = threadIdx.x & 31;
   const WbcConfig& cfg = P.cfg;
   const int nq = NV + 1;
   const double dt = P.io.dt;
+  const double inv_dt = 1.0 / dt;       // the reference divides by dt; multiplying by 1/dt differs by <= 1 ulp
   double* M0 = ws + L.m0;
   double* As = ws + L.m1;
   double* Jm = ws + L.m1;
@@ -268,7 +281,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
     const double* rg = P.io.ref + sidx * WBC_REF_STRIDE;
     if (lane < WBC_REF_STRIDE) io[WBC_IO_REF + lane] = rg[lane];
   }
-  __syncwarp();
+  phase_sync<PS>();
 
   // ---------------------------------------------------------------- kinematics
   warp_fk(M, qs, oMi, lane);
@@ -318,7 +331,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
     Jcom[0] = (sm * Sc[0] - cx[0]) / Mt;
     Jcom[1] = (sm * Sc[1] - cx[1]) / Mt;
   }
-  __syncwarp();
+  phase_sync<PS>();
 
   // ---------------------------------------------------------------- task rows for my column (registers)
   double a[36];
@@ -356,8 +369,8 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
   if (lane == 5) scipy_quat_from_matrix(oMf + WBC_FRAME_TRUNK * WBC_T_STRIDE, fkq);
   if (lane < 6 && ((cfg.task_mask >> lane) & 1)) {
     double b6[6];
-    if (lane < 5) ee_task_target(cfg, lane, oMf, io, dt, b6);
-    else trunk_task_target(cfg, oMf, fkq, io, dt, b6);
+    if (lane < 5) ee_task_target(cfg, lane, oMf, io, inv_dt, b6);
+    else trunk_task_target(cfg, oMf, fkq, io, inv_dt, b6);
 #pragma unroll
     for (int r = 0; r < 6; ++r) bs[6 * lane + r] = b6[r];
   } else if (lane < 6) {
@@ -389,8 +402,8 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
     const double up[4] = {ip[2] + z_var, ie[0] + var, ie[1] + var, ie[2] + var};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      clbs[row_trunk + r] = ((lo[r] - cur[r]) / dt) * 0.5;
-      cubs[row_trunk + r] = ((up[r] - cur[r]) / dt) * 0.5;
+      clbs[row_trunk + r] = ((lo[r] - cur[r]) * inv_dt) * 0.5;
+      cubs[row_trunk + r] = ((up[r] - cur[r]) * inv_dt) * 0.5;
     }
   }
   if (row_com >= 0 && lane == 0) {                               // CoMConstraint (:669-694)
@@ -398,8 +411,8 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
     const double* RR = oMf + 2 * WBC_T_STRIDE + 9;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      clbs[row_com + r] = ((RR[r] - com_w[r]) / dt) * 0.8;
-      cubs[row_com + r] = ((FL[r] - com_w[r]) / dt) * 0.8;
+      clbs[row_com + r] = ((RR[r] - com_w[r]) * inv_dt) * 0.8;
+      cubs[row_com + r] = ((FL[r] - com_w[r]) * inv_dt) * 0.8;
     }
   }
   if (lane < cfg.n_extra_rows) {
@@ -498,7 +511,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
       Cs[(row_extra + e) * LD + lane] = s;
     }
   }
-  __syncwarp();
+  phase_sync<PS>();
   const double clb_r = (lane < nC) ? clbs[lane] : 0.0;
   const double cub_r = (lane < nC) ? cubs[lane] : 0.0;
 
@@ -517,10 +530,11 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
   QpShared S;
   S.M0 = M0; S.J = Jm; S.C = Cs; S.vx = vx; S.vd = vd; S.vg = vg;
   double x;
-  const QpResult res = warp_qp_solve<NV>(S, NV, LD, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
+  const QpResult res = warp_qp_solve_ct<NV>(S, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
 
-  if (lane < NV) P.io.qdot[sidx * NV + lane] = x;
-  if (lane == 0) {
+  phase_sync<PS>();
+  if (valid && lane < NV) P.io.qdot[sidx * NV + lane] = x;
+  if (valid && lane == 0) {
     P.io.status[sidx] = res.status;
     P.io.iters[sidx] = res.iters;
     if (P.io.active_set) {
@@ -528,7 +542,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
       P.io.active_set[2 * sidx + 1] = res.act_rows;
     }
   }
-  if (P.io.mem_out)
+  if (valid && P.io.mem_out)
     for (int i = lane; i < WBC_MEM_STRIDE; i += 32) P.io.mem_out[sidx * WBC_MEM_STRIDE + i] = io[WBC_IO_MEM + i];
 
   // ---------------------------------------------------------------- integrate + base estimate
@@ -593,6 +607,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
       if (lane < 3) qn[lane] = WPA[lane] - rb[lane];
       __syncwarp();
     }
-    for (int i = lane; i < nq; i += 32) P.io.q_next[sidx * nq + i] = qn[i];
+    if (valid)
+      for (int i = lane; i < nq; i += 32) P.io.q_next[sidx * nq + i] = qn[i];
   }
 }
