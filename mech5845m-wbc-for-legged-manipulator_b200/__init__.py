@@ -14,6 +14,7 @@ from .tree_table import TreeTable
 from .robot_model import RobotModel, EE_FRAME_NAMES, EE_JOINT_NAMES, HIP_WAIST_JOINT_NAMES
 from .qp import QP
 from . import synthetic
+from . import sharding
 
-__all__ = ["RobotModel", "QP", "TreeTable", "WbcError", "build_library", "load_library", "synthetic",
+__all__ = ["RobotModel", "QP", "TreeTable", "WbcError", "build_library", "load_library", "synthetic", "sharding",
            "EE_FRAME_NAMES", "EE_JOINT_NAMES", "HIP_WAIST_JOINT_NAMES"]

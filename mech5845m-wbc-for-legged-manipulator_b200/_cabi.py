@@ -26,6 +26,8 @@ CON_COM, CON_TRUNK, CON_FR, CON_FL, CON_RR, CON_RL, CON_GRIP = 1, 2, 4, 8, 16, 3
 COMPAT_DAMPER_OFF_BY_ONE = 1
 QP_SOLVED, QP_MAXITER, QP_INFEASIBLE, QP_NOT_PD = 0, 1, 2, 4
 STEP_FLAG_PLAIN_INTEGRATE = 1
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
+JT_UNIVERSE, JT_FREEFLYER, JT_REVOLUTE, JT_PRISMATIC = 0, 1, 2, 3
 
 EXPORTS = [
     "wbc_abi_version", "wbc_last_error", "wbc_model_create", "wbc_model_destroy", "wbc_config_rows",

@@ -1,0 +1,147 @@
+"""CPU tests (-m "not gpu") of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/wbc_b200.h declares, the ctypes mirrors have the C layout, host-only entry points behave, and the product
+path fails loudly (no CPU fallback) when there is no CUDA device.  No compute call is made here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "wbc_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import wbc_b200
+    wbc_b200.build_library(force=False)
+    return wbc_b200.load_library()
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(wbc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from wbc_b200 import _cabi
+    declared = _declared_functions()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/wbc_b200.h but not exported"
+    assert sorted(_cabi.EXPORTS) == declared, "the ctypes binding and the header disagree about the entry points"
+    assert lib.wbc_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (wbc_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_header_is_plain_c_and_ctypes_layout_matches(tmp_path):
+    """Compile the header as C (gcc, no CUDA, no torch types) and compare sizeof / offsetof with the ctypes mirrors."""
+    from wbc_b200 import _cabi
+    structs = {"WbcTreeTable": _cabi.WbcTreeTable, "WbcConfig": _cabi.WbcConfig, "WbcStepIO": _cabi.WbcStepIO,
+               "WbcAssembleOut": _cabi.WbcAssembleOut}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for sname, cls in structs.items():
+        lines.append(f'  printf("{sname} %zu\\n", sizeof({sname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{sname}.{fname} %zu\\n", offsetof({sname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for sname, cls in structs.items():
+        assert int(got[sname]) == C.sizeof(cls), sname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{sname}.{fname}"]) == getattr(cls, fname).offset, (sname, fname)
+    text = open(HEADER).read()
+    assert "torch" not in text.lower().replace("pytorch tensors", "") and "at::" not in text and "std::" not in text
+
+
+def test_config_rows_host_helper(lib):
+    """m and nC implied by setTasks / setConstraints (Robot_Wrapper4.py:839-876, 764-836) for the three step patterns."""
+    from wbc_b200 import _cabi as cabi
+    m, nc = C.c_int32(), C.c_int32()
+    cfg = cabi.WbcConfig()
+    all_cart = cabi.TASK_FR | cabi.TASK_FL | cabi.TASK_RR | cabi.TASK_RL | cabi.TASK_GRIP | cabi.TASK_TRUNK
+    feet = cabi.CON_FR | cabi.CON_FL | cabi.CON_RR | cabi.CON_RL
+    cases = [  # (task mask, constraint mask, extra rows, nv) -> (m, nC)
+        (all_cart | cabi.TASK_JOINT, 0, 0, 26, 62, 0),                          # P1 bootstrap, WX200
+        (all_cart | cabi.TASK_JOINT, 0, 0, 25, 61, 0),                          # P1 bootstrap, PX100
+        (cabi.TASK_GRIP | cabi.TASK_JOINT, cabi.CON_TRUNK | feet, 0, 26, 32, 16),   # P2 sim3 tick
+        (all_cart | cabi.TASK_JOINT, cabi.CON_TRUNK | feet, 0, 26, 62, 16),     # P3 benchmark step
+        (all_cart | cabi.TASK_JOINT, cabi.CON_TRUNK | feet | cabi.CON_COM, 12, 26, 62, 30),   # config 3: + extension rows
+        (cabi.TASK_TRUNK, cabi.CON_GRIP, 0, 26, 6, 3),
+    ]
+    for tm, cm, extra, nv, em, enc in cases:
+        cfg.task_mask, cfg.constraint_mask, cfg.n_extra_rows = tm, cm, extra
+        assert lib.wbc_config_rows(C.byref(cfg), nv, C.byref(m), C.byref(nc)) == 0
+        assert (m.value, nc.value) == (em, enc)
+    assert lib.wbc_config_rows(None, 26, C.byref(m), C.byref(nc)) == cabi.ERR_INVALID_ARG
+    assert b"null" in lib.wbc_last_error()
+
+
+def test_argument_validation_precedes_any_cuda_work(lib):
+    """Bad arguments come back as WBC_ERR_INVALID_ARG with a message -- also on a box without a GPU."""
+    from wbc_b200 import _cabi as cabi
+    h = C.c_void_p()
+    assert lib.wbc_model_create(None, C.byref(h)) == cabi.ERR_INVALID_ARG
+    t = cabi.WbcTreeTable()
+    t.njoints, t.nq, t.nv, t.nframes = 1, 7, 6, 6
+    assert lib.wbc_model_create(C.byref(t), C.byref(h)) == cabi.ERR_INVALID_ARG and b"njoints" in lib.wbc_last_error()
+    assert lib.wbc_qp_solve(4, 40, 10, 0, None, None, None, None, None, None, None, None, None, 10, None, None, None,
+                            None, None) == cabi.ERR_INVALID_ARG
+    assert lib.wbc_qp_solve(4, 8, 10, 40, None, None, None, None, None, None, None, None, None, 10, None, None, None,
+                            None, None) == cabi.ERR_UNSUPPORTED
+    assert lib.wbc_step(None, None, None, 1, None) == cabi.ERR_INVALID_ARG
+    assert lib.wbc_fk_jac(None, None, 1, None, 0, 0, None, None, None) == cabi.ERR_INVALID_ARG
+    lib.wbc_model_destroy(None)                      # a no-op, must not crash
+
+
+def test_tree_table_marshalling_matches_json():
+    """TreeTable (host) -> WbcTreeTable (C struct): indices, placements, frame slots 0..4 EE + 5 trunk, limits."""
+    from wbc_b200 import TreeTable, _cabi as cabi
+    from wbc_b200.robot_model import RobotModel, EE_FRAME_NAMES
+    t = TreeTable.load("a1_wx200")
+    slots = [t.getFrameId(n, "FIXED_JOINT") for n in EE_FRAME_NAMES] + [t.getFrameId("imu_joint", "FIXED_JOINT")]
+    T = RobotModel._make_table(t, slots)
+    assert (T.njoints, T.nq, T.nv, T.nframes) == (22, 27, 26, 6)
+    assert list(T.parent[:22]) == list(t.parent) and list(T.idx_v[2:22]) == list(range(6, 26))
+    assert [T.frame_parent[s] for s in range(6)] == [7, 4, 13, 10, 18, 1]
+    assert abs(T.frame_p[4][0] - 0.043) < 1e-15 and abs(T.frame_p[0][2] + 0.2) < 1e-15
+    assert T.jtype[1] == cabi.JT_FREEFLYER and T.jtype[20] == cabi.JT_PRISMATIC
+    assert abs(T.placement_p[14][2] - 0.124175) < 1e-12
+    assert abs(sum(T.mass[j] for j in range(22)) - sum(t.mass)) < 1e-12
+
+
+def test_product_path_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    import wbc_b200
+    with pytest.raises(wbc_b200.WbcError):
+        wbc_b200.RobotModel("a1_wx200", batch=4)
+    with pytest.raises(wbc_b200.WbcError):
+        wbc_b200.QP(np.eye(3), np.zeros(3), -np.ones(3), np.ones(3))
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package, the C sources or the header may name it."""
+    pkg = os.path.join(ROOT, "mech5845m-wbc-for-legged-manipulator_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "oracle." in re.sub(r"#.*|//.*", "", text):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    code = ("import sys; sys.path.insert(0, %r); import wbc_b200; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)
