@@ -260,6 +260,79 @@ __global__ void __launch_bounds__(256) wbc_qp_kernel(const __grid_constant__ QpP
   }
 }
 
+// the same drop-in with the register-resident solver (compile-time nv; wbc_qp_reg.cuh)
+template <int NV>
+__global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__ QpParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  constexpr int n = NV, LD = NV | 1;
+  const int nC = P.nC;
+  const int hs_sz = n * (n + 2) + (n & 1), cs_sz = (nC * LD + 1) & ~1;
+  double* ws = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (hs_sz + cs_sz + 96);
+  double* Hs = ws;
+  double* Cs = ws + hs_sz;
+  double* col = Cs + cs_sz;
+  double* vd = col + 64;
+  for (long long s = (long long)blockIdx.x * wpc + warp; s < P.N; s += (long long)gridDim.x * wpc) {
+    double gk = 0.0;
+    if (P.H) {
+      for (int i = lane; i < n * n; i += 32) Hs[(i / n) * LD + (i % n)] = P.H[s * n * n + i];
+      if (lane < n) gk = P.g[s * n + lane];
+    } else {
+      for (int i = lane; i < n * LD; i += 32) Hs[i] = 0.0;
+      __syncwarp();
+      const double* Ag = P.A + s * (long long)P.m * n;
+      const double* bg = P.b + s * (long long)P.m;
+      for (int r = 0; r < P.m; ++r) {
+        const double ark = (lane < n) ? Ag[r * n + lane] : 0.0;
+        vd[lane] = ark;
+        __syncwarp();
+        if (lane < n) {
+          double* Hrow = Hs + lane * LD;
+          for (int l = 0; l < n; ++l) Hrow[l] += ark * vd[l];
+          gk -= ark * bg[r];
+        }
+        __syncwarp();
+      }
+    }
+    if (nC > 0)
+      for (int i = lane; i < nC * n; i += 32) Cs[(i / n) * LD + (i % n)] = P.C[s * (long long)nC * n + i];
+    const double lbv = (lane < n) ? P.lb[s * n + lane] : 0.0, ubv = (lane < n) ? P.ub[s * n + lane] : 0.0;
+    const double clb = (lane < nC) ? P.Clb[s * nC + lane] : 0.0, cub = (lane < nC) ? P.Cub[s * nC + lane] : 0.0;
+    __syncwarp();
+    double h[NV];
+    const double* Hrow = Hs + (lane < n ? lane : 0) * LD;
+#pragma unroll
+    for (int l = 0; l < NV; ++l) h[l] = (lane < n) ? Hrow[l] : 0.0;
+    const double hdiag = (lane < n) ? Hrow[lane] : 0.0;
+    __syncwarp();
+    QpRegShared S;
+    S.R = Hs; S.col = col; S.vd = vd; S.C = Cs;
+    double x;
+    const QpResult res = warp_qp_solve_reg<NV>(S, h, hdiag, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
+    if (lane < n) P.x[s * n + lane] = x;
+    if (lane == 0) {
+      P.status[s] = res.status;
+      P.iters[s] = res.iters;
+      if (P.active_set) { P.active_set[2 * s] = res.act_box; P.active_set[2 * s + 1] = res.act_rows; }
+    }
+    __syncwarp();
+  }
+}
+
+template <int NV>
+static int launch_qp_reg(const QpParams& P, int sms, cudaStream_t st) {
+  const int LD = NV | 1, wpc = 8;
+  const int per_warp = NV * (NV + 2) + (NV & 1) + ((P.nC * LD + 1) & ~1) + 96;
+  const size_t smem = (size_t)wpc * per_warp * sizeof(double);
+  CUDA_TRY(cudaFuncSetAttribute(wbc_qp_reg_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long need = (P.N + wpc - 1) / wpc;
+  const long long cap = (long long)sms * 2;
+  wbc_qp_reg_kernel<NV><<<(int)(need < cap ? need : cap), wpc * 32, smem, st>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return WBC_OK;
+}
+
 // DFMA-saturating microkernel: 8 independent FMA chains per thread
 __global__ void __launch_bounds__(256) wbc_dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -553,14 +626,18 @@ int wbc_qp_solve(int64_t N, int32_t nv, int32_t m, int32_t nC, const double* A, 
   P.A = haveA ? A : nullptr; P.b = haveA ? b : nullptr; P.H = haveH ? H : nullptr; P.g = haveH ? g : nullptr;
   P.lb = lb; P.ub = ub; P.C = C; P.Clb = Clb; P.Cub = Cub;
   P.x = x; P.status = status; P.iters = iters; P.active_set = (unsigned long long*)active_set;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // the robot sizes get the register-resident solver; any other 1 <= nv <= 32 the run-time-size one
+  if (nv == 26) return launch_qp_reg<26>(P, sms, (cudaStream_t)stream);
+  if (nv == 25) return launch_qp_reg<25>(P, sms, (cudaStream_t)stream);
+  if (nv == 18) return launch_qp_reg<18>(P, sms, (cudaStream_t)stream);
   const int LD = nv | 1;
   const int per_warp = 2 * nv * LD + nC * LD + 96 + ((2 * nv * LD + nC * LD) & 1);
   const int wpc = 8;
   const size_t smem = (size_t)wpc * per_warp * sizeof(double);
   CUDA_TRY(cudaFuncSetAttribute(wbc_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long need = (N + wpc - 1) / wpc;
   const long long cap = (long long)sms * 2;
   wbc_qp_kernel<<<(int)(need < cap ? need : cap), wpc * 32, smem, (cudaStream_t)stream>>>(P);

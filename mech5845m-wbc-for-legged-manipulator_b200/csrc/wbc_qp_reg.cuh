@@ -1,0 +1,395 @@
+// wbc_qp_reg.cuh -- register-resident dual active-set QP solver, one warp per problem (compile-time size).
+//
+//   min 1/2 x^T H x + g^T x   s.t.  lb <= x <= ub,  Clb <= C x <= Cub,      H = A^T A > 0
+//
+// Same method and the same pivoting rules as warp_qp_solve_rt (wbc_qp.cuh) and oracle/qp_wrapper.py
+// (Goldfarb-Idnani; replaces QP.solveQP / solveQPHotstart, wrappers/QP_Wrapper.py:23-73), but the
+// factor J = L^-T Q never lives in shared memory.  A matrix-vector product whose matrix sits in shared
+// memory is capped by the LDS pipe at 16 FMA/clk/SM (a quarter of the FP64 pipe); here every matrix
+// element is a register and shared memory only carries broadcast vectors (one wavefront per load).
+//
+// Data placement:
+//   lane i < NV   Jr[0..NV)  = row i of J            = J^T e_i   -- the "d vector" of box constraint i
+//   lane NV       Jr[0..NV)  = L^-1 g                            -- rides along in the spare lane for x0
+//   lane c < nC   Dr[0..NV)  = J^T C[c]^T                        -- the "d vector" of row constraint c
+//   lane i        x_i, lb_i, ub_i, box status     |  lane c: (C x)_c, Clb_c, Cub_c, row status
+//   lane pos      working-set entry `pos` (constraint id, multiplier, R column slot, 1/R_pos,pos)
+//   shared        R [NV][LD] triangular factor of the inequality block, vd[32] broadcast vector,
+//                 (the same block holds the columns of L while H is factorised), col[32] = 1 / L_kk
+//
+// Consequences:
+//   * H = L L^T is right-looking with broadcast columns; the forward substitutions L^-1 [I | g | C^T] then
+//     run for all right-hand sides at once (one broadcast load feeds two FMAs per lane);
+//   * d = J^T n is never computed: every constraint carries its own d, updated by the same reflector as J;
+//   * the reflector (norm, sigma, beta) is computed redundantly by all lanes from the broadcast d: no warp
+//     reductions in the iteration;
+//   * C x is tracked incrementally (C z = Dr . d2 falls out of the reflector application).
+//   * variables with lb == ub are eliminated before the factorisation (row/column of H replaced by the
+//     identity, g and the row bounds shifted); they are reported as equality-active and counted as one
+//     working-set change each, as the oracle counts them.
+//
+// Partial loops "for j >= iq" are switch jumps into a fully unrolled sequence so that every register
+// index is a compile-time constant.
+#pragma once
+#include "wbc_qp.cuh"
+
+struct QpRegShared {
+  double* R;         // [NV][NV + 2]: columns of L during the factorisation, then R with LD = NV | 1
+  double* col;       // [64], 16-byte aligned
+  double* vd;        // [32], 16-byte aligned
+  const double* C;   // [nC][LD] constraint rows (read once)
+};
+
+#define WBC_IX(j) ((j) < NV ? (j) : 0)
+
+template <int NV>
+__device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
+                                                      const int nC, double g, const double lb, const double ub,
+                                                      const double clb, const double cub, const int max_iter,
+                                                      double& x_out) {
+  constexpr int n = NV;
+  constexpr int LD = NV | 1;
+  constexpr int LC = (NV + 1) & ~1;          // column stride of the stored L (even: 128-bit broadcast loads)
+  static_assert(NV < 32, "lane NV carries L^-1 g");
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < NV;
+  double* __restrict__ R = S.R;
+  double* __restrict__ vd = S.vd;
+  QpResult res;
+  res.status = 0;
+  res.iters = 0;
+
+  double hd = act ? hdiag : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hd = fmax(hd, __shfl_xor_sync(WBC_FULL_MASK, hd, o));
+  const double piv_min = WBC_QP_PIVOT_REL * fmax(hd, 0.0);
+
+  // ---- fixed variables (lb == ub) are eliminated: row/column of H -> identity, g shifted -------------
+  const unsigned eqb = __ballot_sync(WBC_FULL_MASK, act && lb == ub);
+  const bool fixed = (eqb >> lane) & 1u;
+  if (eqb) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if ((eqb >> k) & 1u) {                            // warp-uniform
+        const double xk = __shfl_sync(WBC_FULL_MASK, lb, k);
+        g = fma(h[k], xk, g);
+        h[k] = (lane == k) ? 1.0 : 0.0;
+      } else if (fixed) {
+        h[k] = 0.0;
+      }
+    }
+    if (fixed) g = -lb;
+    res.iters = __popc(eqb);
+  }
+  __syncwarp();
+  vd[lane] = act ? g : 0.0;
+
+  // ---- phase A: H = L L^T, right-looking; column k of L (lane i holds L[i][k]) is stored to shared memory
+  //      (Lc[k][i], 16-byte aligned columns) and broadcast back for the trailing update H[i][j] -= L[i][k] L[j][k]
+  double* __restrict__ Lc = S.R;
+  double* __restrict__ rk = S.col;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double dk = __shfl_sync(WBC_FULL_MASK, h[k], k);
+    if (!(dk > piv_min)) {
+      dk = piv_min > 0.0 ? piv_min : 1.0;
+      res.status |= WBC_QP_NOT_PD;
+    }
+    const double r = rsqrt(dk);
+    const double lik = h[k] * r;
+    if (lane < LC) Lc[k * LC + lane] = lik;
+    if (lane == 0) rk[k] = r;
+    __syncwarp();
+    const double2* c2 = reinterpret_cast<const double2*>(Lc + k * LC);
+#pragma unroll
+    for (int p = (k + 1) / 2; p < (NV + 1) / 2; ++p) {
+      const double2 l2 = c2[p];
+      if (2 * p > k) h[WBC_IX(2 * p)] = fma(-lik, l2.x, h[WBC_IX(2 * p)]);
+      if (2 * p + 1 < NV) h[WBC_IX(2 * p + 1)] = fma(-lik, l2.y, h[WBC_IX(2 * p + 1)]);
+    }
+  }
+
+  // ---- phase B: forward substitutions L^-1 [I | g | C^T], column-oriented, all right-hand sides at once:
+  //      lane i < NV: e_i (-> row i of J = L^-T), lane NV: g, second array: lane c < nC: C[c] with the fixed
+  //      variables' coefficients moved into `shift`
+  double Jr[NV], Dr[NV];
+  double shift = 0.0;                                   // sum_k C[c][k] x_k over the fixed variables
+  {
+    const double* Crow = S.C + (lane < nC ? lane : 0) * LD;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      Jr[j] = (lane == NV) ? vd[j] : ((lane == j) ? 1.0 : 0.0);
+      Dr[j] = (lane < nC) ? Crow[j] : 0.0;
+    }
+    if (eqb) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        if ((eqb >> k) & 1u) {
+          shift = fma(Dr[k], __shfl_sync(WBC_FULL_MASK, lb, k), shift);
+          Dr[k] = 0.0;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double r = rk[k];
+    const double yJ = Jr[k] * r, yD = Dr[k] * r;
+    Jr[k] = yJ;
+    Dr[k] = yD;
+    const double2* c2 = reinterpret_cast<const double2*>(Lc + k * LC);
+#pragma unroll
+    for (int p = (k + 1) / 2; p < (NV + 1) / 2; ++p) {
+      const double2 l2 = c2[p];
+      if (2 * p > k) {
+        Jr[WBC_IX(2 * p)] = fma(-l2.x, yJ, Jr[WBC_IX(2 * p)]);
+        Dr[WBC_IX(2 * p)] = fma(-l2.x, yD, Dr[WBC_IX(2 * p)]);
+      }
+      if (2 * p + 1 < NV) {
+        Jr[WBC_IX(2 * p + 1)] = fma(-l2.y, yJ, Jr[WBC_IX(2 * p + 1)]);
+        Dr[WBC_IX(2 * p + 1)] = fma(-l2.y, yD, Dr[WBC_IX(2 * p + 1)]);
+      }
+    }
+  }
+
+  // ---- |d|^2 of every constraint (invariant under the orthogonal updates), x0 = -J (L^-1 g), C x0 -----
+  double ddJ, ddD, x, ax;
+  {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (j & 1) { a1 = fma(Jr[j], Jr[j], a1); b1 = fma(Dr[j], Dr[j], b1); }
+      else { a0 = fma(Jr[j], Jr[j], a0); b0 = fma(Dr[j], Dr[j], b0); }
+    }
+    ddJ = a0 + a1;
+    ddD = b0 + b1;
+    __syncwarp();
+    if (lane == NV) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) vd[j] = Jr[j];
+    }
+    __syncwarp();
+    double x0 = 0.0, x1 = 0.0, c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const double wj = vd[j];
+      if (j & 1) { x1 = fma(-Jr[j], wj, x1); c1 = fma(-Dr[j], wj, c1); }
+      else { x0 = fma(-Jr[j], wj, x0); c0 = fma(-Dr[j], wj, c0); }
+    }
+    x = fixed ? lb : (x0 + x1);
+    ax = (c0 + c1) + shift;
+    __syncwarp();
+  }
+
+  // ---- working set ----------------------------------------------------------------------------------
+  int iq = 0, p_eq = 0;
+  int ws_c = -1, slot = lane;                // per working-set position (lane = position)
+  double u = 0.0, rinv = 0.0;
+  int bstat = fixed ? 3 : 0, cstat = 0;      // 0 none 1 lower 2 upper 3 eq
+  unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && clb == cub);
+
+  bool done = false;
+#pragma unroll 1
+  while (!done) {
+    int ip, side;
+    bool is_eq = false;
+    // ------------------------------------------------------------ pick the entering constraint
+    if (eq_mask_row) {
+      ip = n + __ffs(eq_mask_row) - 1;
+      eq_mask_row &= eq_mask_row - 1;
+      side = -1; is_eq = true;
+    } else {
+      double best = 0.0;
+      int bidx = 0x7fffffff;
+      int myside_b = -1, myside_c = -1;
+      if (act && bstat == 0) {
+        const double slo = x - lb, sup = ub - x;
+        best = fmin(slo, sup);
+        bidx = lane;
+        myside_b = (slo <= sup) ? -1 : +1;
+      }
+      if (lane < nC && cstat == 0) {
+        const double slo = ax - clb, sup = cub - ax;
+        const double v = fmin(slo, sup);
+        myside_c = (slo <= sup) ? -1 : +1;
+        if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
+      }
+      if (bidx == 0x7fffffff) best = 0.0;
+      warp_argmin(best, bidx);
+      if (!(best < -WBC_QP_FEAS_TOL)) break;                       // primal feasible: optimal
+      ip = bidx;
+      const int src = (ip < n) ? ip : ip - n;
+      side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);
+    }
+    const double sgn = (side > 0) ? -1.0 : 1.0;                    // normal = sgn * a_ip
+    const bool is_box = ip < n;
+    const int owner = is_box ? ip : ip - n;
+    const double dd = __shfl_sync(WBC_FULL_MASK, is_box ? ddJ : ddD, owner);
+    double u_new = 0.0;
+
+    // ------------------------------------------------------------ inner loop (GI step 2)
+#pragma unroll 1
+    while (true) {
+      if (!is_eq && res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; done = true; break; }
+      res.iters++;
+      // broadcast the (unsigned) d vector of the entering constraint
+      if (is_box) {
+        if (lane == owner) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) vd[j] = Jr[j];
+        }
+      } else {
+        if (lane == owner) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) vd[j] = Dr[j];
+        }
+      }
+      __syncwarp();
+      // z = J2 d2, w = D2 d2 (= C z), dd2 = |d2|^2 over columns >= iq
+      double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
+      switch (iq) {
+#define WBC_P1(j) case (j): if ((j) < NV) { const double dj = vd[(j)]; \
+          if ((j) & 1) { z1 = fma(Jr[WBC_IX(j)], dj, z1); w1 = fma(Dr[WBC_IX(j)], dj, w1); e1 = fma(dj, dj, e1); } \
+          else { z0 = fma(Jr[WBC_IX(j)], dj, z0); w0 = fma(Dr[WBC_IX(j)], dj, w0); e0 = fma(dj, dj, e0); } }
+        WBC_REP32_ASC(WBC_P1)
+#undef WBC_P1
+        default: break;
+      }
+      const double z = z0 + z1, w = w0 + w1, dd2 = e0 + e1;
+      // r = R^-1 d1 on the inequality block [p_eq, iq)
+      double rr = (lane < iq) ? sgn * vd[lane] : 0.0;
+#pragma unroll 1
+      for (int k = iq - 1; k >= p_eq; --k) {
+        const int slot_k = __shfl_sync(WBC_FULL_MASK, slot, k);
+        const double rk = __shfl_sync(WBC_FULL_MASK, rr * rinv, k);
+        if (lane == k) rr = rk;
+        else if (lane < k && lane >= p_eq) rr -= R[lane * LD + slot_k] * rk;
+      }
+      // constraint value at x:  s = n.x - bnd  (negative when violated)
+      double s_ip;
+      {
+        const double v_i = __shfl_sync(WBC_FULL_MASK, is_box ? x : ax, owner);
+        const double lo_i = __shfl_sync(WBC_FULL_MASK, is_box ? lb : clb, owner);
+        const double up_i = __shfl_sync(WBC_FULL_MASK, is_box ? ub : cub, owner);
+        s_ip = (side > 0) ? (up_i - v_i) : (v_i - lo_i);
+      }
+      const bool dependent = dd2 <= WBC_QP_DEP_TOL * dd;
+
+      if (is_eq) {
+        if (dependent) {                                             // redundant (or inconsistent) equality
+          if (fabs(s_ip) > 1e-8) res.status |= WBC_QP_INFEASIBLE;
+          __syncwarp();
+          break;
+        }
+        const double t = -s_ip / dd2;
+        x = fma(t * sgn, z, x);
+        ax = fma(t * sgn, w, ax);
+        u_new = t;
+      } else {
+        // dual step length over active inequalities
+        double t1 = INFINITY;
+        int l = 0x7fffffff;
+        if (lane >= p_eq && lane < iq && rr > 0.0) { t1 = u / rr; l = lane; }
+        warp_argmin(t1, l);
+        const double t2 = dependent ? INFINITY : -s_ip / dd2;
+        const double t = fmin(t1, t2);
+        if (!(t < INFINITY)) { res.status |= WBC_QP_INFEASIBLE; done = true; break; }
+        if (lane >= p_eq && lane < iq) u -= t * rr;
+        u_new += t;
+        if (!dependent) {
+          x = fma(t * sgn, z, x);
+          ax = fma(t * sgn, w, ax);
+        }
+        if (dependent || !(t2 <= t1)) {
+          // ---------------------------------------------------- drop working-set position l
+          const int c_drop = __shfl_sync(WBC_FULL_MASK, ws_c, l);
+#pragma unroll 1
+          for (int k = l; k < iq - 1; ++k) {
+            const int slot_k1 = __shfl_sync(WBC_FULL_MASK, slot, k + 1);
+            const double a = R[k * LD + slot_k1], b = R[(k + 1) * LD + slot_k1];
+            const double rho = sqrt(a * a + b * b);
+            const double cg = (rho > 0.0) ? a / rho : 1.0, sg = (rho > 0.0) ? b / rho : 0.0;
+            __syncwarp();                                             // everyone has read a, b before rows k, k+1 change
+            if (lane > k && lane < iq) {
+              const double r0 = R[k * LD + slot], r1 = R[(k + 1) * LD + slot];
+              R[k * LD + slot] = cg * r0 + sg * r1;
+              R[(k + 1) * LD + slot] = -sg * r0 + cg * r1;
+            }
+            switch (k) {
+#define WBC_GV(j) case (j): if ((j) + 1 < NV) { \
+                const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)], d0 = Dr[WBC_IX(j)], d1 = Dr[WBC_IX((j) + 1)]; \
+                Jr[WBC_IX(j)] = cg * j0 + sg * j1; Jr[WBC_IX((j) + 1)] = -sg * j0 + cg * j1; \
+                Dr[WBC_IX(j)] = cg * d0 + sg * d1; Dr[WBC_IX((j) + 1)] = -sg * d0 + cg * d1; } break;
+              WBC_REP32_ASC(WBC_GV)
+#undef WBC_GV
+              default: break;
+            }
+            __syncwarp();
+          }
+          {
+            const int dropped_slot = __shfl_sync(WBC_FULL_MASK, slot, l);
+            const int nc_ = __shfl_down_sync(WBC_FULL_MASK, ws_c, 1);
+            const int nslot = __shfl_down_sync(WBC_FULL_MASK, slot, 1);
+            const double nu = __shfl_down_sync(WBC_FULL_MASK, u, 1);
+            if (lane >= l && lane < iq - 1) { ws_c = nc_; slot = nslot; u = nu; }
+            if (lane == iq - 1) { slot = dropped_slot; ws_c = -1; u = 0.0; }
+            if (lane >= l && lane < iq - 1) rinv = 1.0 / R[lane * LD + slot];
+            if (c_drop < n) { if (lane == c_drop) bstat = 0; }
+            else if (lane == c_drop - n) cstat = 0;
+            iq--;
+          }
+          __syncwarp();
+          continue;                                                   // retry the same candidate
+        }
+      }
+      // -------------------------------------------------------- full step: constraint ip enters at position iq
+      {
+        const double d_iq = vd[iq];                                   // unsigned
+        const double nrm = sqrt(dd2);
+        const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
+        const double v_iq = d_iq + sigma;
+        const double beta = 1.0 / (sigma * v_iq);
+        double jiq = 0.0, diq = 0.0;
+        switch (iq) {
+#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; diq = Dr[WBC_IX(j)]; } break;
+          WBC_REP32_ASC(WBC_PK)
+#undef WBC_PK
+          default: break;
+        }
+        const double nbJ = -beta * fma(sigma, jiq, z);
+        const double nbD = -beta * fma(sigma, diq, w);
+        __syncwarp();                                                 // all lanes have read vd[iq] and vd[lane]
+        if (lane == 0) vd[iq] = v_iq;
+        __syncwarp();
+        switch (iq) {
+#define WBC_P2(j) case (j): if ((j) < NV) { const double vj = vd[(j)]; \
+            Jr[WBC_IX(j)] = fma(nbJ, vj, Jr[WBC_IX(j)]); Dr[WBC_IX(j)] = fma(nbD, vj, Dr[WBC_IX(j)]); }
+          WBC_REP32_ASC(WBC_P2)
+#undef WBC_P2
+          default: break;
+        }
+        if (!is_eq) {                                                 // R column (signed): [d1 ; -sigma]
+          const int slot_new = __shfl_sync(WBC_FULL_MASK, slot, iq);
+          if (lane < iq) R[lane * LD + slot_new] = sgn * vd[lane];
+          if (lane == iq) R[iq * LD + slot_new] = -sgn * sigma;
+        }
+        if (lane == iq) {
+          rinv = -1.0 / (sgn * sigma);
+          ws_c = ip;
+          u = u_new;
+        }
+        const int st = is_eq ? 3 : (side > 0 ? 2 : 1);
+        if (is_box) { if (lane == ip) bstat = st; }
+        else if (lane == owner) cstat = st;
+        iq++;
+        if (is_eq) p_eq = iq;
+        __syncwarp();
+      }
+      break;
+    }
+  }
+
+  x_out = fixed ? lb : x;
+  pack_active_sets(lane, n, nC, bstat, cstat, res);
+  return res;
+}

@@ -9,7 +9,7 @@
 // A never touches HBM; per state the kernel reads q, targets, task memory and references and
 // writes qdot, status, iters (+ optional memory / q_next).
 #pragma once
-#include "wbc_qp.cuh"
+#include "wbc_qp_reg.cuh"
 
 #define WBC_IO_TARGETS 0
 #define WBC_IO_MEM 18
@@ -29,28 +29,29 @@
 
 
 
-struct StepLayout {   // per-warp shared-memory layout in doubles
-  int m0, m1, c, omf, vec, io, total;
+struct StepLayout {   // per-warp shared-memory layout in doubles (every offset even: 16-byte aligned)
+  int hs, ast, col, omf, vec, io, total;
 };
 
 __host__ __device__ inline int wbc_ld(int nv) { return nv | 1; }
-__host__ __device__ inline int wbc_lda(int nv) { return nv + (nv & 1); }
+#define WBC_LDT 38    // doubles per column of the transposed task rows: 304 B = 19 x 16 B, conflict-free 128-bit accesses
 
 __host__ __device__ inline StepLayout step_layout(int nv, int nC) {
   StepLayout L;
   const int ld = wbc_ld(nv);
-  int m0 = nv * ld;
-  const int fk = WBC_MAX_JOINTS * WBC_T_STRIDE;      // oMi scratch aliases M0 (dead before H is written)
-  if (m0 < fk) m0 = fk;
-  int m1 = nv * ld + nC * ld;                          // J followed by C ...
-  const int as = 36 * wbc_lda(nv);                     // ... aliased by the staged task rows As
-  if (m1 < as) m1 = as;
-  L.m0 = 0;
-  L.m1 = m0;
-  L.c = m0 + nv * ld;
-  L.omf = m0 + m1;
-  L.vec = L.omf + WBC_HOT_FRAMES * WBC_T_STRIDE + 2;   // keep 16-byte alignment of what follows
-  L.io = L.vec + 7 * 32 + 16;                          // qs[40] vx vd vg clb cub bs[40]
+  int r0 = nv * (nv + 2);                              // H rows, later the L columns / R factor of the QP ...
+  const int fk = WBC_MAX_JOINTS * WBC_T_STRIDE;        // ... aliased by the oMi scratch (dead before H is written)
+  if (r0 < fk) r0 = fk;
+  r0 = (r0 + 1) & ~1;
+  int r1 = nv * WBC_LDT;                               // transposed task rows AsT, later the constraint rows C
+  if (r1 < nC * ld) r1 = nC * ld;
+  r1 = (r1 + 1) & ~1;
+  L.hs = 0;
+  L.ast = r0;
+  L.col = r0 + r1;
+  L.omf = L.col + 64;
+  L.vec = L.omf + WBC_HOT_FRAMES * WBC_T_STRIDE + 2;   // 6 * 13 + 2 = 80
+  L.io = L.vec + 40 + 32 + 32 + 32 + 40;               // qs[40] vd[32] clb[32] cub[32] bs[40]
   L.total = L.io + WBC_IO_TOTAL + 2;
   L.total = (L.total + 1) & ~1;
   return L;
@@ -249,23 +250,19 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
                                               const bool valid) {
   constexpr bool PS = !DEBUG_OUT;
   constexpr int LD = NV | 1;
-  constexpr int LDA = NV + (NV & 1);
   const int lane = threadIdx.x & 31;
   const WbcConfig& cfg = P.cfg;
   const int nq = NV + 1;
   const double dt = P.io.dt;
   const double inv_dt = 1.0 / dt;       // the reference divides by dt; multiplying by 1/dt differs by <= 1 ulp
-  double* M0 = ws + L.m0;
-  double* As = ws + L.m1;
-  double* Jm = ws + L.m1;
-  double* Cs = ws + L.c;
-  double* oMi = ws + L.m0;
+  double* Hs = ws + L.hs;           // [NV][LD] rows of H; the QP reuses it for its R factor
+  double* AsT = ws + L.ast;         // [NV][WBC_LDT] column k of the Cartesian task rows (36 values)
+  double* Cs = ws + L.ast;          // [nC][LD] constraint rows (after AsT is dead)
+  double* oMi = ws + L.hs;
   double* oMf = ws + L.omf;
   double* qs = ws + L.vec;          // [40]
-  double* vx = qs + 40;
-  double* vd = vx + 32;
-  double* vg = vd + 32;
-  double* clbs = vg + 32;
+  double* vd = qs + 40;             // [32]
+  double* clbs = vd + 32;
   double* cubs = clbs + 32;
   double* bs = cubs + 32;           // [40]
   double* io = ws + L.io;
@@ -429,11 +426,18 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
   if (joint_on && cfg.joint_mode == WBC_JOINT_PREV && lane < NV)               // qpJointb "PREV" (:1216-1217)
     bj = ((1.0 / NV) * qs[(lane < 6) ? lane : lane + 1]) * cfg.joint_task_weight;
 
-  // ---------------------------------------------------------------- stage A rows, then H = A^T A, g = -A^T b
-  __syncwarp();                      // all reads of oMi (aliased by nothing yet) and bs writes are done
+  // ---------------------------------------------------------------- H = A^T A, g = -A^T b
+  // Column `lane` of the 36 Cartesian rows goes to shared memory transposed (AsT[lane][r]); then for every
+  // (task t, supporting column l) pair lane i adds  sum_r A[6t+r][i] A[6t+r][l]  to H[i][l]: three 128-bit
+  // broadcast loads and six FMAs.  Pairs outside the frame's support are structural zeros and are skipped.
+  __syncwarp();                      // all reads of oMi (aliased by Hs) and bs writes are done
   if (lane < NV) {
+    double2* dst = reinterpret_cast<double2*>(AsT + lane * WBC_LDT);
 #pragma unroll
-    for (int r = 0; r < 36; ++r) As[r * LDA + lane] = a[r];
+    for (int r = 0; r < 18; ++r) dst[r] = make_double2(a[2 * r], a[2 * r + 1]);
+    double* Hrow = Hs + lane * LD;
+#pragma unroll
+    for (int l = 0; l < NV; ++l) Hrow[l] = (l == lane) ? aj * aj : 0.0;
   }
   __syncwarp();
   double gk = 0.0;
@@ -442,17 +446,23 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
     for (int r = 0; r < 36; ++r) gk -= a[r] * bs[r];
     gk -= aj * bj;
   }
-  for (int l = 0; l < NV; ++l) {
-    double h = 0.0;
+  {
+    double* Hrow = Hs + (lane < NV ? lane : 0) * LD;
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
-      if (((cfg.task_mask >> t) & 1) && ((M->frame_supp[t] >> l) & 1u)) {     // warp-uniform: skip structural zeros
-#pragma unroll
-        for (int r = 0; r < 6; ++r) h += a[6 * t + r] * As[(6 * t + r) * LDA + l];
+      if (!((cfg.task_mask >> t) & 1)) continue;
+      uint32_t mask = M->frame_supp[t];
+      while (mask) {                                               // warp-uniform
+        const int l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double2* c2 = reinterpret_cast<const double2*>(AsT + l * WBC_LDT + 6 * t);
+        const double2 v0 = c2[0], v1 = c2[1], v2 = c2[2];
+        double h0 = a[6 * t] * v0.x, h1 = a[6 * t + 1] * v0.y;
+        h0 = fma(a[6 * t + 2], v1.x, h0); h1 = fma(a[6 * t + 3], v1.y, h1);
+        h0 = fma(a[6 * t + 4], v2.x, h0); h1 = fma(a[6 * t + 5], v2.y, h1);
+        if (lane < NV) Hrow[l] += h0 + h1;
       }
     }
-    if (l == lane) h += aj * aj;
-    if (lane < NV) M0[lane * LD + l] = h;
   }
   __syncwarp();
 
@@ -464,7 +474,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
       for (int t = 0; t < 6; ++t) {
         if (!((cfg.task_mask >> t) & 1)) continue;
         for (int r = 0; r < 6; ++r, ++row) {
-          if (D.A) D.A[(sidx * m + row) * NV + lane] = As[(6 * t + r) * LDA + lane];
+          if (D.A) D.A[(sidx * m + row) * NV + lane] = AsT[lane * WBC_LDT + 6 * t + r];
           if (D.b && lane == 0) D.b[sidx * m + row] = bs[6 * t + r];
         }
       }
@@ -478,12 +488,12 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
       if (D.ub) D.ub[sidx * NV + lane] = ubv;
       if (D.g) D.g[sidx * NV + lane] = gk;
       if (D.H)
-        for (int l = 0; l < NV; ++l) D.H[(sidx * NV + lane) * NV + l] = M0[lane * LD + l];
+        for (int l = 0; l < NV; ++l) D.H[(sidx * NV + lane) * NV + l] = Hs[lane * LD + l];
     }
     __syncwarp();
   }
 
-  // ---------------------------------------------------------------- constraint rows (As is dead now)
+  // ---------------------------------------------------------------- constraint rows (AsT is dead now)
   if (lane < NV) {
     if (row_com >= 0) { Cs[(row_com + 0) * LD + lane] = Jcom[0]; Cs[(row_com + 1) * LD + lane] = Jcom[1]; }
     if (row_trunk >= 0) {                                        // LWA rows z, wx, wy, wz of the trunk frame (:709)
@@ -527,10 +537,19 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
   }
 
   // ---------------------------------------------------------------- QP
-  QpShared S;
-  S.M0 = M0; S.J = Jm; S.C = Cs; S.vx = vx; S.vd = vd; S.vg = vg;
   double x;
-  const QpResult res = warp_qp_solve_ct<NV>(S, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
+  QpResult res;
+  {
+    double h[NV];
+    const double* Hrow = Hs + (lane < NV ? lane : 0) * LD;
+#pragma unroll
+    for (int l = 0; l < NV; ++l) h[l] = (lane < NV) ? Hrow[l] : 0.0;
+    const double hdiag = (lane < NV) ? Hrow[lane] : 0.0;
+    __syncwarp();                    // Hs becomes the solver's R factor
+    QpRegShared S;
+    S.R = Hs; S.col = ws + L.col; S.vd = vd; S.C = Cs;
+    res = warp_qp_solve_reg<NV>(S, h, hdiag, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
+  }
 
   phase_sync<PS>();
   if (valid && lane < NV) P.io.qdot[sidx * NV + lane] = x;
@@ -552,7 +571,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
     double vb[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) vb[i] = __shfl_sync(WBC_FULL_MASK, v, i);
-    double* qn = vx;                 // [<= 33] new configuration (vx, vd are contiguous: 64 doubles)
+    double* qn = ws + L.col;         // [<= 33] new configuration (the 64-double column buffer is free now)
     if (lane == 0) {
       double o7[7];
       integrate_freeflyer(qs, vb, o7);
