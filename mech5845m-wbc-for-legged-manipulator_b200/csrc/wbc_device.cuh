@@ -47,6 +47,36 @@ struct DevModel {
 };
 
 // ------------------------------------------------------------------------------------------------
+// explicit shared-memory access through 32-bit shared-window addresses
+// ------------------------------------------------------------------------------------------------
+// ptxas rematerialises the address of a dynamic-shared-memory element (S2UR SR_CgaCtaId, ULEA, IMAD, LEA ...,
+// up to 15 instructions) in front of every access inside switch-case blocks instead of keeping one register
+// live (seen in the SASS of the first register-resident solver).  The hot loops therefore address shared
+// memory as  [base + immediate]  with `base` a 32-bit register that went through a self-shuffle, which
+// ptxas cannot recompute.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  return (uint32_t)__shfl_sync(WBC_FULL_MASK, (int)a, threadIdx.x & 31);
+}
+// (a constant added to `a` after unrolling is folded into the instruction's immediate offset by ptxas)
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3x3 helpers (row-major)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {

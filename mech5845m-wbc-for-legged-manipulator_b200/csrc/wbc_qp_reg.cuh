@@ -28,19 +28,28 @@
 //     identity, g and the row bounds shifted); they are reported as equality-active and counted as one
 //     working-set change each, as the oracle counts them.
 //
-// Partial loops "for j >= iq" are switch jumps into a fully unrolled sequence so that every register
-// index is a compile-time constant.
+// Partial sums "over j >= iq" are full-length static loops over a broadcast vector whose first iq entries
+// were zeroed in shared memory (one predicated store), so every register index is a compile-time constant and
+// the passes are straight-line code.  Shared memory is addressed as [32-bit base + immediate] (wbc_device.cuh).
 #pragma once
 #include "wbc_qp.cuh"
 
 struct QpRegShared {
   double* R;         // [NV][NV + 2]: columns of L during the factorisation, then R with LD = NV | 1
-  double* col;       // [64], 16-byte aligned
-  double* vd;        // [32], 16-byte aligned
+  double* col;       // [64], 16-byte aligned: 1 / L_kk
+  double* vd;        // [32], 16-byte aligned: broadcast vector
   const double* C;   // [nC][LD] constraint rows (read once)
 };
 
 #define WBC_IX(j) ((j) < NV ? (j) : 0)
+
+// lane `owner` publishes its NV register values as vd[0..NV) (zero padded to an even count)
+template <int NV>
+__device__ __forceinline__ void publish_row(uint32_t vd_a, const double (&a)[NV]) {
+#pragma unroll
+  for (int p = 0; p < (NV + 1) / 2; ++p)
+    sts_f64x2(vd_a + 16 * p, a[2 * p], (2 * p + 1 < NV) ? a[WBC_IX(2 * p + 1)] : 0.0);
+}
 
 template <int NV>
 __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
@@ -50,11 +59,13 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   constexpr int n = NV;
   constexpr int LD = NV | 1;
   constexpr int LC = (NV + 1) & ~1;          // column stride of the stored L (even: 128-bit broadcast loads)
+  constexpr int NP = (NV + 1) / 2;           // pairs per vector
   static_assert(NV < 32, "lane NV carries L^-1 g");
   const int lane = threadIdx.x & 31;
   const bool act = lane < NV;
-  double* __restrict__ R = S.R;
-  double* __restrict__ vd = S.vd;
+  const uint32_t R_a = smem_addr(S.R);       // also the columns of L
+  const uint32_t vd_a = smem_addr(S.vd);
+  const uint32_t rk_a = smem_addr(S.col);
   QpResult res;
   res.status = 0;
   res.iters = 0;
@@ -82,12 +93,10 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     res.iters = __popc(eqb);
   }
   __syncwarp();
-  vd[lane] = act ? g : 0.0;
+  sts_f64(vd_a + 8 * lane, act ? g : 0.0);
 
   // ---- phase A: H = L L^T, right-looking; column k of L (lane i holds L[i][k]) is stored to shared memory
   //      (Lc[k][i], 16-byte aligned columns) and broadcast back for the trailing update H[i][j] -= L[i][k] L[j][k]
-  double* __restrict__ Lc = S.R;
-  double* __restrict__ rk = S.col;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     double dk = __shfl_sync(WBC_FULL_MASK, h[k], k);
@@ -97,13 +106,12 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     }
     const double r = rsqrt(dk);
     const double lik = h[k] * r;
-    if (lane < LC) Lc[k * LC + lane] = lik;
-    if (lane == 0) rk[k] = r;
+    if (lane < LC) sts_f64(R_a + 8 * (k * LC + lane), lik);
+    if (lane == 0) sts_f64(rk_a + 8 * k, r);
     __syncwarp();
-    const double2* c2 = reinterpret_cast<const double2*>(Lc + k * LC);
 #pragma unroll
-    for (int p = (k + 1) / 2; p < (NV + 1) / 2; ++p) {
-      const double2 l2 = c2[p];
+    for (int p = (k + 1) / 2; p < NP; ++p) {
+      const double2 l2 = lds_f64x2(R_a + 8 * (k * LC + 2 * p));
       if (2 * p > k) h[WBC_IX(2 * p)] = fma(-lik, l2.x, h[WBC_IX(2 * p)]);
       if (2 * p + 1 < NV) h[WBC_IX(2 * p + 1)] = fma(-lik, l2.y, h[WBC_IX(2 * p + 1)]);
     }
@@ -115,11 +123,12 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   double Jr[NV], Dr[NV];
   double shift = 0.0;                                   // sum_k C[c][k] x_k over the fixed variables
   {
-    const double* Crow = S.C + (lane < nC ? lane : 0) * LD;
+    const uint32_t crow_a = smem_addr(S.C) + 8 * ((lane < nC ? lane : 0) * LD);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      Jr[j] = (lane == NV) ? vd[j] : ((lane == j) ? 1.0 : 0.0);
-      Dr[j] = (lane < nC) ? Crow[j] : 0.0;
+      const double gj = lds_f64(vd_a + 8 * j), cj = lds_f64(crow_a + 8 * j);
+      Jr[j] = (lane == NV) ? gj : ((lane == j) ? 1.0 : 0.0);
+      Dr[j] = (lane < nC) ? cj : 0.0;
     }
     if (eqb) {
 #pragma unroll
@@ -133,14 +142,13 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   }
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const double r = rk[k];
+    const double r = lds_f64(rk_a + 8 * k);
     const double yJ = Jr[k] * r, yD = Dr[k] * r;
     Jr[k] = yJ;
     Dr[k] = yD;
-    const double2* c2 = reinterpret_cast<const double2*>(Lc + k * LC);
 #pragma unroll
-    for (int p = (k + 1) / 2; p < (NV + 1) / 2; ++p) {
-      const double2 l2 = c2[p];
+    for (int p = (k + 1) / 2; p < NP; ++p) {
+      const double2 l2 = lds_f64x2(R_a + 8 * (k * LC + 2 * p));
       if (2 * p > k) {
         Jr[WBC_IX(2 * p)] = fma(-l2.x, yJ, Jr[WBC_IX(2 * p)]);
         Dr[WBC_IX(2 * p)] = fma(-l2.x, yD, Dr[WBC_IX(2 * p)]);
@@ -164,17 +172,18 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     ddJ = a0 + a1;
     ddD = b0 + b1;
     __syncwarp();
-    if (lane == NV) {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) vd[j] = Jr[j];
-    }
+    if (lane == NV) publish_row<NV>(vd_a, Jr);
     __syncwarp();
     double x0 = 0.0, x1 = 0.0, c0 = 0.0, c1 = 0.0;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const double wj = vd[j];
-      if (j & 1) { x1 = fma(-Jr[j], wj, x1); c1 = fma(-Dr[j], wj, c1); }
-      else { x0 = fma(-Jr[j], wj, x0); c0 = fma(-Dr[j], wj, c0); }
+    for (int p = 0; p < NP; ++p) {
+      const double2 w2 = lds_f64x2(vd_a + 16 * p);
+      x0 = fma(-Jr[2 * p], w2.x, x0);
+      c0 = fma(-Dr[2 * p], w2.x, c0);
+      if (2 * p + 1 < NV) {
+        x1 = fma(-Jr[WBC_IX(2 * p + 1)], w2.y, x1);
+        c1 = fma(-Dr[WBC_IX(2 * p + 1)], w2.y, c1);
+      }
     }
     x = fixed ? lb : (x0 + x1);
     ax = (c0 + c1) + shift;
@@ -232,38 +241,39 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     while (true) {
       if (!is_eq && res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; done = true; break; }
       res.iters++;
-      // broadcast the (unsigned) d vector of the entering constraint
-      if (is_box) {
-        if (lane == owner) {
-#pragma unroll
-          for (int j = 0; j < NV; ++j) vd[j] = Jr[j];
-        }
-      } else {
-        if (lane == owner) {
-#pragma unroll
-          for (int j = 0; j < NV; ++j) vd[j] = Dr[j];
-        }
+      // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
+      if (lane == owner) {
+        if (is_box) publish_row<NV>(vd_a, Jr);
+        else publish_row<NV>(vd_a, Dr);
       }
       __syncwarp();
-      // z = J2 d2, w = D2 d2 (= C z), dd2 = |d2|^2 over columns >= iq
+      const double d_own = lds_f64(vd_a + 8 * lane);
+      __syncwarp();
+      if (lane < iq) sts_f64(vd_a + 8 * lane, 0.0);
+      __syncwarp();
+      // z = J2 d2, w = D2 d2 (= C z), dd2 = |d2|^2
       double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
-      switch (iq) {
-#define WBC_P1(j) case (j): if ((j) < NV) { const double dj = vd[(j)]; \
-          if ((j) & 1) { z1 = fma(Jr[WBC_IX(j)], dj, z1); w1 = fma(Dr[WBC_IX(j)], dj, w1); e1 = fma(dj, dj, e1); } \
-          else { z0 = fma(Jr[WBC_IX(j)], dj, z0); w0 = fma(Dr[WBC_IX(j)], dj, w0); e0 = fma(dj, dj, e0); } }
-        WBC_REP32_ASC(WBC_P1)
-#undef WBC_P1
-        default: break;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const double2 d2 = lds_f64x2(vd_a + 16 * p);
+        z0 = fma(Jr[2 * p], d2.x, z0);
+        w0 = fma(Dr[2 * p], d2.x, w0);
+        e0 = fma(d2.x, d2.x, e0);
+        if (2 * p + 1 < NV) {
+          z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
+          w1 = fma(Dr[WBC_IX(2 * p + 1)], d2.y, w1);
+          e1 = fma(d2.y, d2.y, e1);
+        }
       }
       const double z = z0 + z1, w = w0 + w1, dd2 = e0 + e1;
       // r = R^-1 d1 on the inequality block [p_eq, iq)
-      double rr = (lane < iq) ? sgn * vd[lane] : 0.0;
+      double rr = (lane < iq) ? sgn * d_own : 0.0;
 #pragma unroll 1
       for (int k = iq - 1; k >= p_eq; --k) {
         const int slot_k = __shfl_sync(WBC_FULL_MASK, slot, k);
         const double rk = __shfl_sync(WBC_FULL_MASK, rr * rinv, k);
         if (lane == k) rr = rk;
-        else if (lane < k && lane >= p_eq) rr -= R[lane * LD + slot_k] * rk;
+        else if (lane < k && lane >= p_eq) rr -= lds_f64(R_a + 8 * (lane * LD + slot_k)) * rk;
       }
       // constraint value at x:  s = n.x - bnd  (negative when violated)
       double s_ip;
@@ -278,7 +288,6 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       if (is_eq) {
         if (dependent) {                                             // redundant (or inconsistent) equality
           if (fabs(s_ip) > 1e-8) res.status |= WBC_QP_INFEASIBLE;
-          __syncwarp();
           break;
         }
         const double t = -s_ip / dd2;
@@ -306,14 +315,15 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
 #pragma unroll 1
           for (int k = l; k < iq - 1; ++k) {
             const int slot_k1 = __shfl_sync(WBC_FULL_MASK, slot, k + 1);
-            const double a = R[k * LD + slot_k1], b = R[(k + 1) * LD + slot_k1];
+            const double a = lds_f64(R_a + 8 * (k * LD + slot_k1)), b = lds_f64(R_a + 8 * ((k + 1) * LD + slot_k1));
             const double rho = sqrt(a * a + b * b);
             const double cg = (rho > 0.0) ? a / rho : 1.0, sg = (rho > 0.0) ? b / rho : 0.0;
             __syncwarp();                                             // everyone has read a, b before rows k, k+1 change
             if (lane > k && lane < iq) {
-              const double r0 = R[k * LD + slot], r1 = R[(k + 1) * LD + slot];
-              R[k * LD + slot] = cg * r0 + sg * r1;
-              R[(k + 1) * LD + slot] = -sg * r0 + cg * r1;
+              const uint32_t a0 = R_a + 8 * (k * LD + slot), a1 = R_a + 8 * ((k + 1) * LD + slot);
+              const double r0 = lds_f64(a0), r1 = lds_f64(a1);
+              sts_f64(a0, cg * r0 + sg * r1);
+              sts_f64(a1, -sg * r0 + cg * r1);
             }
             switch (k) {
 #define WBC_GV(j) case (j): if ((j) + 1 < NV) { \
@@ -333,7 +343,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
             const double nu = __shfl_down_sync(WBC_FULL_MASK, u, 1);
             if (lane >= l && lane < iq - 1) { ws_c = nc_; slot = nslot; u = nu; }
             if (lane == iq - 1) { slot = dropped_slot; ws_c = -1; u = 0.0; }
-            if (lane >= l && lane < iq - 1) rinv = 1.0 / R[lane * LD + slot];
+            if (lane >= l && lane < iq - 1) rinv = 1.0 / lds_f64(R_a + 8 * (lane * LD + slot));
             if (c_drop < n) { if (lane == c_drop) bstat = 0; }
             else if (lane == c_drop - n) cstat = 0;
             iq--;
@@ -344,7 +354,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       }
       // -------------------------------------------------------- full step: constraint ip enters at position iq
       {
-        const double d_iq = vd[iq];                                   // unsigned
+        const double d_iq = __shfl_sync(WBC_FULL_MASK, d_own, iq);    // unsigned
         const double nrm = sqrt(dd2);
         const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
         const double v_iq = d_iq + sigma;
@@ -358,20 +368,22 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
         }
         const double nbJ = -beta * fma(sigma, jiq, z);
         const double nbD = -beta * fma(sigma, diq, w);
-        __syncwarp();                                                 // all lanes have read vd[iq] and vd[lane]
-        if (lane == 0) vd[iq] = v_iq;
+        if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);                  // vd = v = d2 + sigma e_iq (zeros below iq)
         __syncwarp();
-        switch (iq) {
-#define WBC_P2(j) case (j): if ((j) < NV) { const double vj = vd[(j)]; \
-            Jr[WBC_IX(j)] = fma(nbJ, vj, Jr[WBC_IX(j)]); Dr[WBC_IX(j)] = fma(nbD, vj, Dr[WBC_IX(j)]); }
-          WBC_REP32_ASC(WBC_P2)
-#undef WBC_P2
-          default: break;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const double2 v2 = lds_f64x2(vd_a + 16 * p);
+          Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
+          Dr[2 * p] = fma(nbD, v2.x, Dr[2 * p]);
+          if (2 * p + 1 < NV) {
+            Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
+            Dr[WBC_IX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_IX(2 * p + 1)]);
+          }
         }
         if (!is_eq) {                                                 // R column (signed): [d1 ; -sigma]
           const int slot_new = __shfl_sync(WBC_FULL_MASK, slot, iq);
-          if (lane < iq) R[lane * LD + slot_new] = sgn * vd[lane];
-          if (lane == iq) R[iq * LD + slot_new] = -sgn * sigma;
+          if (lane < iq) sts_f64(R_a + 8 * (lane * LD + slot_new), sgn * d_own);
+          if (lane == iq) sts_f64(R_a + 8 * (iq * LD + slot_new), -sgn * sigma);
         }
         if (lane == iq) {
           rinv = -1.0 / (sgn * sigma);
@@ -387,6 +399,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       }
       break;
     }
+    __syncwarp();
   }
 
   x_out = fixed ? lb : x;
