@@ -13,7 +13,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libwbc_b200.so")
+LIB_PATH = os.environ.get("WBC_B200_LIB") or os.path.join(PKG_DIR, "libwbc_b200.so")   # override: A/B builds only
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "wbc_b200.h")
 
 MAX_JOINTS, MAX_NV, MAX_NQ, MAX_FRAMES, NUM_EE, MAX_NC, MAX_EXTRA = 32, 32, 33, 16, 5, 32, 16

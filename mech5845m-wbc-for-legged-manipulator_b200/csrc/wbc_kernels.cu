@@ -39,9 +39,16 @@ __device__ __forceinline__ void stage_model(const DevModel* __restrict__ g, DevM
   __syncthreads();
 }
 
-// fused tick / assembly accessor: persistent CTAs, one state per warp
-template <int NV, bool DEBUG_OUT>
-__global__ void __launch_bounds__(384, 1) wbc_step_kernel(const __grid_constant__ StepParams P) {
+// fused tick / assembly accessor: persistent CTAs, one state per warp.
+// SPLIT (nC <= 16): the QP keeps each row's d vector in two lanes, fits 168 registers -> 12 warps per SM;
+// otherwise the full-width layout needs ~210 registers -> 8 warps per SM.
+#ifndef WBC_STEP_WARPS
+#define WBC_STEP_WARPS 12
+#endif
+template <bool SPLIT> struct StepWarps { static constexpr int value = SPLIT ? WBC_STEP_WARPS : 8; };
+
+template <int NV, bool DEBUG_OUT, bool SPLIT>
+__global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, 1) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
   stage_model(P.model, Ms);
@@ -54,7 +61,7 @@ __global__ void __launch_bounds__(384, 1) wbc_step_kernel(const __grid_constant_
     const bool valid = s < P.N;          // padding warps shadow the last state so that block barriers stay uniform
     if (!valid) s = P.N - 1;
     if (DEBUG_OUT && !valid) continue;
-    warp_wbc_step<NV, DEBUG_OUT>(P, Ms, ws, L, s, valid);
+    warp_wbc_step<NV, DEBUG_OUT, SPLIT>(P, Ms, ws, L, s, valid);
     __syncwarp();
   }
 }
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(256) wbc_qp_kernel(const __grid_constant__ QpP
 }
 
 // the same drop-in with the register-resident solver (compile-time nv; wbc_qp_reg.cuh)
-template <int NV>
+template <int NV, bool SPLIT>
 __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__ QpParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
     QpRegShared S;
     S.R = Hs; S.col = col; S.vd = vd; S.C = Cs;
     double x;
-    const QpResult res = warp_qp_solve_reg<NV>(S, h, hdiag, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
+    const QpResult res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
     if (lane < n) P.x[s * n + lane] = x;
     if (lane == 0) {
       P.status[s] = res.status;
@@ -320,17 +327,22 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
   }
 }
 
-template <int NV>
-static int launch_qp_reg(const QpParams& P, int sms, cudaStream_t st) {
+template <int NV, bool SPLIT>
+static int launch_qp_reg_k(const QpParams& P, int sms, cudaStream_t st) {
   const int LD = NV | 1, wpc = 8;
   const int per_warp = NV * (NV + 2) + (NV & 1) + ((P.nC * LD + 1) & ~1) + 96;
   const size_t smem = (size_t)wpc * per_warp * sizeof(double);
-  CUDA_TRY(cudaFuncSetAttribute(wbc_qp_reg_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = wbc_qp_reg_kernel<NV, SPLIT>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + wpc - 1) / wpc;
   const long long cap = (long long)sms * 2;
-  wbc_qp_reg_kernel<NV><<<(int)(need < cap ? need : cap), wpc * 32, smem, st>>>(P);
+  kern<<<(int)(need < cap ? need : cap), wpc * 32, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
   return WBC_OK;
+}
+template <int NV>
+static int launch_qp_reg(const QpParams& P, int sms, cudaStream_t st) {
+  return P.nC <= 16 ? launch_qp_reg_k<NV, true>(P, sms, st) : launch_qp_reg_k<NV, false>(P, sms, st);
 }
 
 // DFMA-saturating microkernel: 8 independent FMA chains per thread
@@ -415,17 +427,17 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
 
 static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15); }
 
-template <int NV, bool DBG>
-static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
+template <int NV, bool DBG, bool SPLIT>
+static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
   const StepLayout L = step_layout(NV, P.nC);
   const size_t per_warp = (size_t)L.total * sizeof(double);
   int max_optin = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, model->device));
   int warps = (int)(((size_t)max_optin - model_smem_bytes()) / per_warp);
-  if (warps > 12) warps = 12;
+  if (warps > StepWarps<SPLIT>::value) warps = StepWarps<SPLIT>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
   const size_t smem = model_smem_bytes() + warps * per_warp;
-  auto kern = wbc_step_kernel<NV, DBG>;
+  auto kern = wbc_step_kernel<NV, DBG, SPLIT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + warps - 1) / warps;
   int grid = (int)(need < model->sm_count ? need : model->sm_count);
@@ -440,6 +452,12 @@ static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_
   kern<<<grid, warps * 32, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
   return WBC_OK;
+}
+
+template <int NV, bool DBG>
+static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
+  if (DBG) return launch_step_k<NV, DBG, true>(model, P, st, info);      // the accessor never reaches the solver
+  return P.nC <= 16 ? launch_step_k<NV, DBG, true>(model, P, st, info) : launch_step_k<NV, DBG, false>(model, P, st, info);
 }
 
 template <bool DBG>

@@ -12,6 +12,8 @@
 //   lane i < NV   Jr[0..NV)  = row i of J            = J^T e_i   -- the "d vector" of box constraint i
 //   lane NV       Jr[0..NV)  = L^-1 g                            -- rides along in the spare lane for x0
 //   lane c < nC   Dr[0..NV)  = J^T C[c]^T                        -- the "d vector" of row constraint c
+//                 (SPLIT, nC <= 16: lane c holds elements [0, HALF) and lane c + 16 elements [HALF, NV) of it,
+//                  which frees 2 * (NV - HALF) registers per thread and a quarter of the FMAs of every pass)
 //   lane i        x_i, lb_i, ub_i, box status     |  lane c: (C x)_c, Clb_c, Cub_c, row status
 //   lane pos      working-set entry `pos` (constraint id, multiplier, R column slot, 1/R_pos,pos)
 //   shared        R [NV][LD] triangular factor of the inequality block, vd[32] broadcast vector,
@@ -42,16 +44,17 @@ struct QpRegShared {
 };
 
 #define WBC_IX(j) ((j) < NV ? (j) : 0)
+#define WBC_DX(j) (((j) >= 0 && (j) < ND) ? (j) : 0)
 
-// lane `owner` publishes its NV register values as vd[0..NV) (zero padded to an even count)
-template <int NV>
-__device__ __forceinline__ void publish_row(uint32_t vd_a, const double (&a)[NV]) {
+// the calling lane publishes N register values as a[0..N) at shared address `a0` (zero padded to an even count)
+template <int N>
+__device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
 #pragma unroll
-  for (int p = 0; p < (NV + 1) / 2; ++p)
-    sts_f64x2(vd_a + 16 * p, a[2 * p], (2 * p + 1 < NV) ? a[WBC_IX(2 * p + 1)] : 0.0);
+  for (int p = 0; p < (N + 1) / 2; ++p)
+    sts_f64x2(a0 + 16 * p, a[2 * p], (2 * p + 1 < N) ? a[(2 * p + 1 < N) ? 2 * p + 1 : 0] : 0.0);
 }
 
-template <int NV>
+template <int NV, bool SPLIT>
 __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
                                                       const int nC, double g, const double lb, const double ub,
                                                       const double clb, const double cub, const int max_iter,
@@ -60,12 +63,19 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   constexpr int LD = NV | 1;
   constexpr int LC = (NV + 1) & ~1;          // column stride of the stored L (even: 128-bit broadcast loads)
   constexpr int NP = (NV + 1) / 2;           // pairs per vector
+  constexpr int HALF = SPLIT ? ((((NV + 1) / 2) + 1) & ~1) : NV;   // elements of a row's d vector per lane
+  constexpr int ND = HALF;
   static_assert(NV < 32, "lane NV carries L^-1 g");
+  static_assert(!SPLIT || (2 * HALF <= 32 && NV - HALF <= HALF), "split layout");
   const int lane = threadIdx.x & 31;
   const bool act = lane < NV;
+  const bool upper = SPLIT && lane >= 16;    // this lane holds the second half of its row's d vector
+  const int crow = SPLIT ? (lane & 15) : lane;
+  const bool has_row = crow < nC;
   const uint32_t R_a = smem_addr(S.R);       // also the columns of L
   const uint32_t vd_a = smem_addr(S.vd);
   const uint32_t rk_a = smem_addr(S.col);
+  const uint32_t doff = upper ? 8u * HALF : 0u;   // byte offset of this lane's segment inside a broadcast vector
   QpResult res;
   res.status = 0;
   res.iters = 0;
@@ -93,7 +103,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     res.iters = __popc(eqb);
   }
   __syncwarp();
-  sts_f64(vd_a + 8 * lane, act ? g : 0.0);
+  sts_f64(vd_a + 8 * lane, act ? g : 0.0);              // also zeroes the padding vd[NV..32)
 
   // ---- phase A: H = L L^T, right-looking; column k of L (lane i holds L[i][k]) is stored to shared memory
   //      (Lc[k][i], 16-byte aligned columns) and broadcast back for the trailing update H[i][j] -= L[i][k] L[j][k]
@@ -118,44 +128,75 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   }
 
   // ---- phase B: forward substitutions L^-1 [I | g | C^T], column-oriented, all right-hand sides at once:
-  //      lane i < NV: e_i (-> row i of J = L^-T), lane NV: g, second array: lane c < nC: C[c] with the fixed
+  //      lane i < NV: e_i (-> row i of J = L^-T), lane NV: g, second array: the rows of C with the fixed
   //      variables' coefficients moved into `shift`
-  double Jr[NV], Dr[NV];
+  double Jr[NV], Dr[ND];
   double shift = 0.0;                                   // sum_k C[c][k] x_k over the fixed variables
   {
-    const uint32_t crow_a = smem_addr(S.C) + 8 * ((lane < nC ? lane : 0) * LD);
+    const uint32_t crow_a = smem_addr(S.C) + 8 * ((has_row ? crow : 0) * LD) + doff;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const double gj = lds_f64(vd_a + 8 * j), cj = lds_f64(crow_a + 8 * j);
+      const double gj = lds_f64(vd_a + 8 * j);
       Jr[j] = (lane == NV) ? gj : ((lane == j) ? 1.0 : 0.0);
-      Dr[j] = (lane < nC) ? cj : 0.0;
+    }
+#pragma unroll
+    for (int jl = 0; jl < ND; ++jl) {
+      // (a lower lane reads C[c][jl], an upper lane C[c][HALF + jl]; reads past the row are discarded)
+      const double cj = lds_f64(crow_a + 8 * jl);
+      Dr[jl] = (has_row && (!upper || jl + HALF < NV)) ? cj : 0.0;
     }
     if (eqb) {
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         if ((eqb >> k) & 1u) {
-          shift = fma(Dr[k], __shfl_sync(WBC_FULL_MASK, lb, k), shift);
-          Dr[k] = 0.0;
+          const double xk = __shfl_sync(WBC_FULL_MASK, lb, k);
+          const bool holder = !SPLIT || (upper == (k >= HALF));
+          const int kl = (SPLIT && k >= HALF) ? k - HALF : k;
+          if (holder) {
+            shift = fma(Dr[WBC_DX(kl)], xk, shift);
+            Dr[WBC_DX(kl)] = 0.0;
+          }
         }
       }
+      if (SPLIT) shift += __shfl_xor_sync(WBC_FULL_MASK, shift, 16);
     }
   }
+  {
+    const uint32_t Lb = R_a + doff;                     // this lane's segment of a column of L
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const double r = lds_f64(rk_a + 8 * k);
-    const double yJ = Jr[k] * r, yD = Dr[k] * r;
-    Jr[k] = yJ;
-    Dr[k] = yD;
-#pragma unroll
-    for (int p = (k + 1) / 2; p < NP; ++p) {
-      const double2 l2 = lds_f64x2(R_a + 8 * (k * LC + 2 * p));
-      if (2 * p > k) {
-        Jr[WBC_IX(2 * p)] = fma(-l2.x, yJ, Jr[WBC_IX(2 * p)]);
-        Dr[WBC_IX(2 * p)] = fma(-l2.x, yD, Dr[WBC_IX(2 * p)]);
+    for (int k = 0; k < NV; ++k) {
+      const double r = lds_f64(rk_a + 8 * k);
+      const double yJ = Jr[k] * r;
+      Jr[k] = yJ;
+      const int kl = (SPLIT && k >= HALF) ? k - HALF : k;
+      double yD = Dr[WBC_DX(kl)] * r;
+      if (SPLIT) {
+        const bool holder = upper == (k >= HALF);
+        if (holder) Dr[WBC_DX(kl)] = yD;
+        yD = __shfl_sync(WBC_FULL_MASK, yD, crow + (k >= HALF ? 16 : 0));
+      } else {
+        Dr[WBC_DX(kl)] = yD;
       }
-      if (2 * p + 1 < NV) {
-        Jr[WBC_IX(2 * p + 1)] = fma(-l2.y, yJ, Jr[WBC_IX(2 * p + 1)]);
-        Dr[WBC_IX(2 * p + 1)] = fma(-l2.y, yD, Dr[WBC_IX(2 * p + 1)]);
+#pragma unroll
+      for (int p = (k + 1) / 2; p < NP; ++p) {
+        const double2 l2 = lds_f64x2(R_a + 8 * (k * LC + 2 * p));
+        if (2 * p > k) Jr[WBC_IX(2 * p)] = fma(-l2.x, yJ, Jr[WBC_IX(2 * p)]);
+        if (2 * p + 1 < NV) Jr[WBC_IX(2 * p + 1)] = fma(-l2.y, yJ, Jr[WBC_IX(2 * p + 1)]);
+      }
+      // second array: element jl of a lower lane is column jl, of an upper lane column HALF + jl
+#pragma unroll
+      for (int pl = 0; pl < ND / 2 + (ND & 1); ++pl) {
+        const int j0 = 2 * pl, j1 = 2 * pl + 1;
+        const bool lv0 = j0 > k, lv1 = j1 > k && j1 < ND;
+        const bool uv0 = SPLIT && (j0 + HALF > k) && (j0 + HALF < NV), uv1 = SPLIT && j1 < ND && (j1 + HALF > k) && (j1 + HALF < NV);
+        if (!(lv0 || lv1 || uv0 || uv1)) continue;
+        const double2 l2 = lds_f64x2(Lb + 8 * (k * LC + 2 * pl));
+        if (lv0 && (uv0 || !SPLIT)) Dr[WBC_DX(j0)] = fma(-l2.x, yD, Dr[WBC_DX(j0)]);
+        else if (lv0) { if (!upper) Dr[WBC_DX(j0)] = fma(-l2.x, yD, Dr[WBC_DX(j0)]); }
+        else if (uv0) { if (upper) Dr[WBC_DX(j0)] = fma(-l2.x, yD, Dr[WBC_DX(j0)]); }
+        if (lv1 && (uv1 || !SPLIT)) Dr[WBC_DX(j1)] = fma(-l2.y, yD, Dr[WBC_DX(j1)]);
+        else if (lv1) { if (!upper) Dr[WBC_DX(j1)] = fma(-l2.y, yD, Dr[WBC_DX(j1)]); }
+        else if (uv1) { if (upper) Dr[WBC_DX(j1)] = fma(-l2.y, yD, Dr[WBC_DX(j1)]); }
       }
     }
   }
@@ -166,11 +207,17 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      if (j & 1) { a1 = fma(Jr[j], Jr[j], a1); b1 = fma(Dr[j], Dr[j], b1); }
-      else { a0 = fma(Jr[j], Jr[j], a0); b0 = fma(Dr[j], Dr[j], b0); }
+      if (j & 1) a1 = fma(Jr[j], Jr[j], a1);
+      else a0 = fma(Jr[j], Jr[j], a0);
+    }
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      if (j & 1) b1 = fma(Dr[j], Dr[j], b1);
+      else b0 = fma(Dr[j], Dr[j], b0);
     }
     ddJ = a0 + a1;
     ddD = b0 + b1;
+    if (SPLIT) ddD += __shfl_xor_sync(WBC_FULL_MASK, ddD, 16);
     __syncwarp();
     if (lane == NV) publish_row<NV>(vd_a, Jr);
     __syncwarp();
@@ -179,14 +226,18 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     for (int p = 0; p < NP; ++p) {
       const double2 w2 = lds_f64x2(vd_a + 16 * p);
       x0 = fma(-Jr[2 * p], w2.x, x0);
+      if (2 * p + 1 < NV) x1 = fma(-Jr[WBC_IX(2 * p + 1)], w2.y, x1);
+    }
+#pragma unroll
+    for (int p = 0; p < (ND + 1) / 2; ++p) {
+      const double2 w2 = lds_f64x2(vd_a + doff + 16 * p);
       c0 = fma(-Dr[2 * p], w2.x, c0);
-      if (2 * p + 1 < NV) {
-        x1 = fma(-Jr[WBC_IX(2 * p + 1)], w2.y, x1);
-        c1 = fma(-Dr[WBC_IX(2 * p + 1)], w2.y, c1);
-      }
+      if (2 * p + 1 < ND) c1 = fma(-Dr[WBC_DX(2 * p + 1)], w2.y, c1);
     }
     x = fixed ? lb : (x0 + x1);
-    ax = (c0 + c1) + shift;
+    double cx = c0 + c1;
+    if (SPLIT) cx += __shfl_xor_sync(WBC_FULL_MASK, cx, 16);
+    ax = cx + shift;
     __syncwarp();
   }
 
@@ -242,9 +293,10 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       if (!is_eq && res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; done = true; break; }
       res.iters++;
       // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
-      if (lane == owner) {
-        if (is_box) publish_row<NV>(vd_a, Jr);
-        else publish_row<NV>(vd_a, Dr);
+      if (is_box) {
+        if (lane == owner) publish_row<NV>(vd_a, Jr);
+      } else {
+        if (crow == owner) publish_row<ND>(vd_a + doff, Dr);       // SPLIT: both halves write their segment
       }
       __syncwarp();
       const double d_own = lds_f64(vd_a + 8 * lane);
@@ -257,15 +309,25 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       for (int p = 0; p < NP; ++p) {
         const double2 d2 = lds_f64x2(vd_a + 16 * p);
         z0 = fma(Jr[2 * p], d2.x, z0);
-        w0 = fma(Dr[2 * p], d2.x, w0);
         e0 = fma(d2.x, d2.x, e0);
+        if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
         if (2 * p + 1 < NV) {
           z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
-          w1 = fma(Dr[WBC_IX(2 * p + 1)], d2.y, w1);
           e1 = fma(d2.y, d2.y, e1);
+          if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
         }
       }
-      const double z = z0 + z1, w = w0 + w1, dd2 = e0 + e1;
+      if (SPLIT) {
+#pragma unroll
+        for (int p = 0; p < ND / 2; ++p) {
+          const double2 d2 = lds_f64x2(vd_a + doff + 16 * p);
+          w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+          w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+        }
+      }
+      double w = w0 + w1;
+      if (SPLIT) w += __shfl_xor_sync(WBC_FULL_MASK, w, 16);
+      const double z = z0 + z1, dd2 = e0 + e1;
       // r = R^-1 d1 on the inequality block [p_eq, iq)
       double rr = (lane < iq) ? sgn * d_own : 0.0;
 #pragma unroll 1
@@ -325,11 +387,22 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
               sts_f64(a0, cg * r0 + sg * r1);
               sts_f64(a1, -sg * r0 + cg * r1);
             }
+            // rotate columns k, k + 1 of J and of the rows' d vectors
             switch (k) {
 #define WBC_GV(j) case (j): if ((j) + 1 < NV) { \
-                const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)], d0 = Dr[WBC_IX(j)], d1 = Dr[WBC_IX((j) + 1)]; \
+                const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)]; \
                 Jr[WBC_IX(j)] = cg * j0 + sg * j1; Jr[WBC_IX((j) + 1)] = -sg * j0 + cg * j1; \
-                Dr[WBC_IX(j)] = cg * d0 + sg * d1; Dr[WBC_IX((j) + 1)] = -sg * d0 + cg * d1; } break;
+                if (!SPLIT || (j) + 1 < HALF) { \
+                  if (!upper) { const double d0 = Dr[WBC_DX(j)], d1 = Dr[WBC_DX((j) + 1)]; \
+                    Dr[WBC_DX(j)] = cg * d0 + sg * d1; Dr[WBC_DX((j) + 1)] = -sg * d0 + cg * d1; } \
+                } else if ((j) >= HALF) { \
+                  if (upper) { const double d0 = Dr[WBC_DX((j) - HALF)], d1 = Dr[WBC_DX((j) + 1 - HALF)]; \
+                    Dr[WBC_DX((j) - HALF)] = cg * d0 + sg * d1; Dr[WBC_DX((j) + 1 - HALF)] = -sg * d0 + cg * d1; } \
+                } else {   /* j == HALF - 1: column j sits in the lower lane, column j + 1 in the upper lane */ \
+                  const double mine = upper ? Dr[0] : Dr[WBC_DX(HALF - 1)]; \
+                  const double other = __shfl_xor_sync(WBC_FULL_MASK, mine, 16); \
+                  if (upper) Dr[0] = -sg * other + cg * mine; else Dr[WBC_DX(HALF - 1)] = cg * mine + sg * other; \
+                } } break;
               WBC_REP32_ASC(WBC_GV)
 #undef WBC_GV
               default: break;
@@ -360,12 +433,16 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
         const double v_iq = d_iq + sigma;
         const double beta = 1.0 / (sigma * v_iq);
         double jiq = 0.0, diq = 0.0;
-        switch (iq) {
-#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; diq = Dr[WBC_IX(j)]; } break;
+        switch (iq) {                                                 // column iq of J and of the rows' d vectors
+#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; \
+            if (!SPLIT) diq = Dr[WBC_DX(j)]; \
+            else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
+            else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
           WBC_REP32_ASC(WBC_PK)
 #undef WBC_PK
           default: break;
         }
+        if (SPLIT) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
         const double nbJ = -beta * fma(sigma, jiq, z);
         const double nbD = -beta * fma(sigma, diq, w);
         if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);                  // vd = v = d2 + sigma e_iq (zeros below iq)
@@ -374,10 +451,18 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
         for (int p = 0; p < NP; ++p) {
           const double2 v2 = lds_f64x2(vd_a + 16 * p);
           Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
-          Dr[2 * p] = fma(nbD, v2.x, Dr[2 * p]);
+          if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
           if (2 * p + 1 < NV) {
             Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
-            Dr[WBC_IX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_IX(2 * p + 1)]);
+            if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
+          }
+        }
+        if (SPLIT) {
+#pragma unroll
+          for (int p = 0; p < ND / 2; ++p) {
+            const double2 v2 = lds_f64x2(vd_a + doff + 16 * p);
+            Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+            Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
           }
         }
         if (!is_eq) {                                                 // R column (signed): [d1 ; -sigma]

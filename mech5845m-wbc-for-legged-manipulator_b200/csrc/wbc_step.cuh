@@ -244,7 +244,7 @@ __device__ __forceinline__ void phase_sync() {
   else __syncwarp();
 }
 
-template <int NV, bool DEBUG_OUT>
+template <int NV, bool DEBUG_OUT, bool SPLIT>
 __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevModel* __restrict__ M,
                                               double* __restrict__ ws, const StepLayout L, long long sidx,
                                               const bool valid) {
@@ -548,7 +548,7 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
     __syncwarp();                    // Hs becomes the solver's R factor
     QpRegShared S;
     S.R = Hs; S.col = ws + L.col; S.vd = vd; S.C = Cs;
-    res = warp_qp_solve_reg<NV>(S, h, hdiag, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
+    res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
   }
 
   phase_sync<PS>();
