@@ -45,10 +45,16 @@ __device__ __forceinline__ void stage_model(const DevModel* __restrict__ g, DevM
 #ifndef WBC_STEP_WARPS
 #define WBC_STEP_WARPS 12
 #endif
-template <bool SPLIT> struct StepWarps { static constexpr int value = SPLIT ? WBC_STEP_WARPS : 8; };
+#ifndef WBC_STEP_CTAS
+#define WBC_STEP_CTAS 1       // CTAs per SM of the SPLIT kernel (WBC_STEP_WARPS warps each)
+#endif
+template <bool SPLIT> struct StepWarps {
+  static constexpr int value = SPLIT ? WBC_STEP_WARPS : 8;
+  static constexpr int ctas = SPLIT ? WBC_STEP_CTAS : 1;
+};
 
 template <int NV, bool DEBUG_OUT, bool SPLIT>
-__global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, 1) wbc_step_kernel(const __grid_constant__ StepParams P) {
+__global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>::ctas) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
   stage_model(P.model, Ms);
@@ -433,19 +439,20 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
   const size_t per_warp = (size_t)L.total * sizeof(double);
   int max_optin = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, model->device));
-  int warps = (int)(((size_t)max_optin - model_smem_bytes()) / per_warp);
+  constexpr int ctas = StepWarps<SPLIT>::ctas;
+  int warps = (int)(((size_t)(max_optin + 1024) / ctas - 1024 - model_smem_bytes()) / per_warp);
   if (warps > StepWarps<SPLIT>::value) warps = StepWarps<SPLIT>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
   const size_t smem = model_smem_bytes() + warps * per_warp;
   auto kern = wbc_step_kernel<NV, DBG, SPLIT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + warps - 1) / warps;
-  int grid = (int)(need < model->sm_count ? need : model->sm_count);
+  int grid = (int)(need < (long long)model->sm_count * ctas ? need : (long long)model->sm_count * ctas);
   if (grid < 1) grid = 1;
   if (info) {
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
-    info[0] = model->sm_count; info[1] = warps * 32; info[2] = (int)smem; info[3] = fa.numRegs;
+    info[0] = model->sm_count * ctas; info[1] = warps * 32; info[2] = (int)smem; info[3] = fa.numRegs;
     return WBC_OK;
   }
   if (P.N == 0) return WBC_OK;

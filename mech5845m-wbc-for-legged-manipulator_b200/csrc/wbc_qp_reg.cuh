@@ -43,6 +43,28 @@ struct QpRegShared {
   const double* C;   // [nC][LD] constraint rows (read once)
 };
 
+// 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free
+// (the library rsqrt()/division carry a slow path for denormals that costs convergence barriers and
+// ~30 dependent instructions in the middle of every iteration).  Relative error <= ~2 ulp.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);                      // 1 - x y^2
+  y = fma(y * fma(e, 0.375, 0.5), e, y);               // y (1 + e/2 + 3 e^2/8)
+  e = fma(-x * y, y, 1.0);
+  y = fma(y * 0.5, e, y);
+  return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, fma(e, e, e), y);                         // y (1 + e + e^2)
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
 #define WBC_IX(j) ((j) < NV ? (j) : 0)
 #define WBC_DX(j) (((j) >= 0 && (j) < ND) ? (j) : 0)
 
@@ -114,7 +136,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       dk = piv_min > 0.0 ? piv_min : 1.0;
       res.status |= WBC_QP_NOT_PD;
     }
-    const double r = rsqrt(dk);
+    const double r = fast_rsqrt(dk);
     const double lik = h[k] * r;
     if (lane < LC) sts_f64(R_a + 8 * (k * LC + lane), lik);
     if (lane == 0) sts_f64(rk_a + 8 * k, r);
@@ -183,7 +205,9 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
         if (2 * p > k) Jr[WBC_IX(2 * p)] = fma(-l2.x, yJ, Jr[WBC_IX(2 * p)]);
         if (2 * p + 1 < NV) Jr[WBC_IX(2 * p + 1)] = fma(-l2.y, yJ, Jr[WBC_IX(2 * p + 1)]);
       }
-      // second array: element jl of a lower lane is column jl, of an upper lane column HALF + jl
+      // second array: element jl of a lower lane is column jl, of an upper lane column HALF + jl; elements that
+      // only one half updates use a multiplier that is zero in the other half (no per-element selects)
+      const double yD_lo = upper ? 0.0 : yD, yD_up = upper ? yD : 0.0;
 #pragma unroll
       for (int pl = 0; pl < ND / 2 + (ND & 1); ++pl) {
         const int j0 = 2 * pl, j1 = 2 * pl + 1;
@@ -191,12 +215,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
         const bool uv0 = SPLIT && (j0 + HALF > k) && (j0 + HALF < NV), uv1 = SPLIT && j1 < ND && (j1 + HALF > k) && (j1 + HALF < NV);
         if (!(lv0 || lv1 || uv0 || uv1)) continue;
         const double2 l2 = lds_f64x2(Lb + 8 * (k * LC + 2 * pl));
-        if (lv0 && (uv0 || !SPLIT)) Dr[WBC_DX(j0)] = fma(-l2.x, yD, Dr[WBC_DX(j0)]);
-        else if (lv0) { if (!upper) Dr[WBC_DX(j0)] = fma(-l2.x, yD, Dr[WBC_DX(j0)]); }
-        else if (uv0) { if (upper) Dr[WBC_DX(j0)] = fma(-l2.x, yD, Dr[WBC_DX(j0)]); }
-        if (lv1 && (uv1 || !SPLIT)) Dr[WBC_DX(j1)] = fma(-l2.y, yD, Dr[WBC_DX(j1)]);
-        else if (lv1) { if (!upper) Dr[WBC_DX(j1)] = fma(-l2.y, yD, Dr[WBC_DX(j1)]); }
-        else if (uv1) { if (upper) Dr[WBC_DX(j1)] = fma(-l2.y, yD, Dr[WBC_DX(j1)]); }
+        if (lv0 || uv0) Dr[WBC_DX(j0)] = fma(-l2.x, (lv0 && (uv0 || !SPLIT)) ? yD : (lv0 ? yD_lo : yD_up), Dr[WBC_DX(j0)]);
+        if (lv1 || uv1) Dr[WBC_DX(j1)] = fma(-l2.y, (lv1 && (uv1 || !SPLIT)) ? yD : (lv1 ? yD_lo : yD_up), Dr[WBC_DX(j1)]);
       }
     }
   }
@@ -248,241 +268,245 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   int bstat = fixed ? 3 : 0, cstat = 0;      // 0 none 1 lower 2 upper 3 eq
   unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && clb == cub);
 
-  bool done = false;
+  // One flat loop: every pass is one step of the method for the current candidate (pick one if there is none).
+  bool have = false, is_eq = false, is_box = false;
+  int ip = 0, side = -1, owner = 0;
+  double sgn = 1.0, dd = 0.0, u_new = 0.0;
 #pragma unroll 1
-  while (!done) {
-    int ip, side;
-    bool is_eq = false;
-    // ------------------------------------------------------------ pick the entering constraint
-    if (eq_mask_row) {
-      ip = n + __ffs(eq_mask_row) - 1;
-      eq_mask_row &= eq_mask_row - 1;
-      side = -1; is_eq = true;
-    } else {
-      double best = 0.0;
-      int bidx = 0x7fffffff;
-      int myside_b = -1, myside_c = -1;
-      if (act && bstat == 0) {
-        const double slo = x - lb, sup = ub - x;
-        best = fmin(slo, sup);
-        bidx = lane;
-        myside_b = (slo <= sup) ? -1 : +1;
-      }
-      if (lane < nC && cstat == 0) {
-        const double slo = ax - clb, sup = cub - ax;
-        const double v = fmin(slo, sup);
-        myside_c = (slo <= sup) ? -1 : +1;
-        if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
-      }
-      if (bidx == 0x7fffffff) best = 0.0;
-      warp_argmin(best, bidx);
-      if (!(best < -WBC_QP_FEAS_TOL)) break;                       // primal feasible: optimal
-      ip = bidx;
-      const int src = (ip < n) ? ip : ip - n;
-      side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);
-    }
-    const double sgn = (side > 0) ? -1.0 : 1.0;                    // normal = sgn * a_ip
-    const bool is_box = ip < n;
-    const int owner = is_box ? ip : ip - n;
-    const double dd = __shfl_sync(WBC_FULL_MASK, is_box ? ddJ : ddD, owner);
-    double u_new = 0.0;
-
-    // ------------------------------------------------------------ inner loop (GI step 2)
-#pragma unroll 1
-    while (true) {
-      if (!is_eq && res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; done = true; break; }
-      res.iters++;
-      // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
-      if (is_box) {
-        if (lane == owner) publish_row<NV>(vd_a, Jr);
+  for (;;) {
+    if (!have) {
+      // ------------------------------------------------------------ pick the entering constraint
+      if (eq_mask_row) {
+        ip = n + __ffs(eq_mask_row) - 1;
+        eq_mask_row &= eq_mask_row - 1;
+        side = -1; is_eq = true;
       } else {
-        if (crow == owner) publish_row<ND>(vd_a + doff, Dr);       // SPLIT: both halves write their segment
+        is_eq = false;
+        double best = 0.0;
+        int bidx = 0x7fffffff;
+        int myside_b = -1, myside_c = -1;
+        if (act && bstat == 0) {
+          const double slo = x - lb, sup = ub - x;
+          best = fmin(slo, sup);
+          bidx = lane;
+          myside_b = (slo <= sup) ? -1 : +1;
+        }
+        if (lane < nC && cstat == 0) {
+          const double slo = ax - clb, sup = cub - ax;
+          const double v = fmin(slo, sup);
+          myside_c = (slo <= sup) ? -1 : +1;
+          if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
+        }
+        if (bidx == 0x7fffffff) best = 0.0;
+        warp_argmin(best, bidx);
+        if (!(best < -WBC_QP_FEAS_TOL)) break;                     // primal feasible: optimal
+        ip = bidx;
+        const int src = (ip < n) ? ip : ip - n;
+        side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);
       }
+      sgn = (side > 0) ? -1.0 : 1.0;                               // normal = sgn * a_ip
+      is_box = ip < n;
+      owner = is_box ? ip : ip - n;
+      dd = __shfl_sync(WBC_FULL_MASK, is_box ? ddJ : ddD, owner);
+      u_new = 0.0;
+      have = true;
+    }
+    if (!is_eq && res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; break; }
+    res.iters++;
+    // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
+    if (is_box) {
+      if (lane == owner) publish_row<NV>(vd_a, Jr);
+    } else {
+      if (crow == owner) publish_row<ND>(vd_a + doff, Dr);         // SPLIT: both halves write their segment
+    }
+    __syncwarp();
+    const double d_own = lds_f64(vd_a + 8 * lane);
+    __syncwarp();
+    if (lane < iq) sts_f64(vd_a + 8 * lane, 0.0);
+    __syncwarp();
+    // z = J2 d2, w = D2 d2 (= C z), dd2 = |d2|^2
+    double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const double2 d2 = lds_f64x2(vd_a + 16 * p);
+      z0 = fma(Jr[2 * p], d2.x, z0);
+      e0 = fma(d2.x, d2.x, e0);
+      if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+      if (2 * p + 1 < NV) {
+        z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
+        e1 = fma(d2.y, d2.y, e1);
+        if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+      }
+    }
+    if (SPLIT) {
+#pragma unroll
+      for (int p = 0; p < ND / 2; ++p) {
+        const double2 d2 = lds_f64x2(vd_a + doff + 16 * p);
+        w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+        w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+      }
+    }
+    double w = w0 + w1;
+    if (SPLIT) w += __shfl_xor_sync(WBC_FULL_MASK, w, 16);
+    const double z = z0 + z1, dd2 = e0 + e1;
+    // r = R^-1 d1 on the inequality block [p_eq, iq)
+    double rr = (lane < iq) ? sgn * d_own : 0.0;
+#pragma unroll 1
+    for (int k = iq - 1; k >= p_eq; --k) {
+      const int slot_k = __shfl_sync(WBC_FULL_MASK, slot, k);
+      const double rk = __shfl_sync(WBC_FULL_MASK, rr * rinv, k);
+      if (lane == k) rr = rk;
+      else if (lane < k && lane >= p_eq) rr -= lds_f64(R_a + 8 * (lane * LD + slot_k)) * rk;
+    }
+    // constraint value at x:  s = n.x - bnd  (negative when violated)
+    double s_ip;
+    {
+      const double v_i = __shfl_sync(WBC_FULL_MASK, is_box ? x : ax, owner);
+      const double lo_i = __shfl_sync(WBC_FULL_MASK, is_box ? lb : clb, owner);
+      const double up_i = __shfl_sync(WBC_FULL_MASK, is_box ? ub : cub, owner);
+      s_ip = (side > 0) ? (up_i - v_i) : (v_i - lo_i);
+    }
+    const bool dependent = dd2 <= WBC_QP_DEP_TOL * dd;
+    // 1 / |d2|, shared by the step length and the reflector (dd2 > 0 unless dependent: then unused)
+    const double rs = fast_rsqrt(fmax(dd2, 1e-300));
+    const double t2 = dependent ? INFINITY : -s_ip * (rs * rs);
+    bool add = false;
+
+    if (is_eq) {
+      if (dependent) {                                               // redundant (or inconsistent) equality
+        if (fabs(s_ip) > 1e-8) res.status |= WBC_QP_INFEASIBLE;
+        have = false;
+      } else {
+        x = fma(t2 * sgn, z, x);
+        ax = fma(t2 * sgn, w, ax);
+        u_new = t2;
+        add = true;
+      }
+    } else {
+      // dual step length over active inequalities
+      double t1 = INFINITY;
+      int l = 0x7fffffff;
+      if (lane >= p_eq && lane < iq && rr > 0.0) { t1 = u / rr; l = lane; }
+      warp_argmin(t1, l);
+      const double t = fmin(t1, t2);
+      if (!(t < INFINITY)) { res.status |= WBC_QP_INFEASIBLE; break; }
+      if (lane >= p_eq && lane < iq) u -= t * rr;
+      u_new += t;
+      if (!dependent) {
+        x = fma(t * sgn, z, x);
+        ax = fma(t * sgn, w, ax);
+      }
+      if (dependent || !(t2 <= t1)) {
+        // ------------------------------------------------------ drop working-set position l, keep the candidate
+        const int c_drop = __shfl_sync(WBC_FULL_MASK, ws_c, l);
+#pragma unroll 1
+        for (int k = l; k < iq - 1; ++k) {
+          const int slot_k1 = __shfl_sync(WBC_FULL_MASK, slot, k + 1);
+          const double a = lds_f64(R_a + 8 * (k * LD + slot_k1)), b = lds_f64(R_a + 8 * ((k + 1) * LD + slot_k1));
+          const double rho = sqrt(a * a + b * b);
+          const double cg = (rho > 0.0) ? a / rho : 1.0, sg = (rho > 0.0) ? b / rho : 0.0;
+          __syncwarp();                                               // everyone has read a, b before rows k, k+1 change
+          if (lane > k && lane < iq) {
+            const uint32_t a0 = R_a + 8 * (k * LD + slot), a1 = R_a + 8 * ((k + 1) * LD + slot);
+            const double r0 = lds_f64(a0), r1 = lds_f64(a1);
+            sts_f64(a0, cg * r0 + sg * r1);
+            sts_f64(a1, -sg * r0 + cg * r1);
+          }
+          // rotate columns k, k + 1 of J and of the rows' d vectors
+          switch (k) {
+#define WBC_GV(j) case (j): if ((j) + 1 < NV) { \
+              const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)]; \
+              Jr[WBC_IX(j)] = cg * j0 + sg * j1; Jr[WBC_IX((j) + 1)] = -sg * j0 + cg * j1; \
+              if (!SPLIT || (j) + 1 < HALF) { \
+                if (!upper) { const double d0 = Dr[WBC_DX(j)], d1 = Dr[WBC_DX((j) + 1)]; \
+                  Dr[WBC_DX(j)] = cg * d0 + sg * d1; Dr[WBC_DX((j) + 1)] = -sg * d0 + cg * d1; } \
+              } else if ((j) >= HALF) { \
+                if (upper) { const double d0 = Dr[WBC_DX((j) - HALF)], d1 = Dr[WBC_DX((j) + 1 - HALF)]; \
+                  Dr[WBC_DX((j) - HALF)] = cg * d0 + sg * d1; Dr[WBC_DX((j) + 1 - HALF)] = -sg * d0 + cg * d1; } \
+              } else {   /* j == HALF - 1: column j sits in the lower lane, column j + 1 in the upper lane */ \
+                const double mine = upper ? Dr[0] : Dr[WBC_DX(HALF - 1)]; \
+                const double other = __shfl_xor_sync(WBC_FULL_MASK, mine, 16); \
+                if (upper) Dr[0] = -sg * other + cg * mine; else Dr[WBC_DX(HALF - 1)] = cg * mine + sg * other; \
+              } } break;
+            WBC_REP32_ASC(WBC_GV)
+#undef WBC_GV
+            default: break;
+          }
+          __syncwarp();
+        }
+        {
+          const int dropped_slot = __shfl_sync(WBC_FULL_MASK, slot, l);
+          const int nc_ = __shfl_down_sync(WBC_FULL_MASK, ws_c, 1);
+          const int nslot = __shfl_down_sync(WBC_FULL_MASK, slot, 1);
+          const double nu = __shfl_down_sync(WBC_FULL_MASK, u, 1);
+          if (lane >= l && lane < iq - 1) { ws_c = nc_; slot = nslot; u = nu; }
+          if (lane == iq - 1) { slot = dropped_slot; ws_c = -1; u = 0.0; }
+          if (lane >= l && lane < iq - 1) rinv = 1.0 / lds_f64(R_a + 8 * (lane * LD + slot));
+          if (c_drop < n) { if (lane == c_drop) bstat = 0; }
+          else if (lane == c_drop - n) cstat = 0;
+          iq--;
+        }
+      } else {
+        add = true;
+      }
+    }
+    if (add) {
+      // -------------------------------------------------------- full step: constraint ip enters at position iq
+      const double d_iq = __shfl_sync(WBC_FULL_MASK, d_own, iq);      // unsigned
+      const double nrm = dd2 * rs;
+      const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
+      const double isig = (d_iq >= 0.0) ? rs : -rs;                   // 1 / sigma
+      const double v_iq = d_iq + sigma;
+      const double beta = isig * fast_rcp(v_iq);                      // 1 / (sigma v_iq)
+      double jiq = 0.0, diq = 0.0;
+      switch (iq) {                                                   // column iq of J and of the rows' d vectors
+#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; \
+          if (!SPLIT) diq = Dr[WBC_DX(j)]; \
+          else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
+          else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
+        WBC_REP32_ASC(WBC_PK)
+#undef WBC_PK
+        default: break;
+      }
+      if (SPLIT) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
+      const double nbJ = -beta * fma(sigma, jiq, z);
+      const double nbD = -beta * fma(sigma, diq, w);
+      if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);                    // vd = v = d2 + sigma e_iq (zeros below iq)
       __syncwarp();
-      const double d_own = lds_f64(vd_a + 8 * lane);
-      __syncwarp();
-      if (lane < iq) sts_f64(vd_a + 8 * lane, 0.0);
-      __syncwarp();
-      // z = J2 d2, w = D2 d2 (= C z), dd2 = |d2|^2
-      double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        const double2 d2 = lds_f64x2(vd_a + 16 * p);
-        z0 = fma(Jr[2 * p], d2.x, z0);
-        e0 = fma(d2.x, d2.x, e0);
-        if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+        const double2 v2 = lds_f64x2(vd_a + 16 * p);
+        Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
+        if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
         if (2 * p + 1 < NV) {
-          z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
-          e1 = fma(d2.y, d2.y, e1);
-          if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+          Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
+          if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
         }
       }
       if (SPLIT) {
 #pragma unroll
         for (int p = 0; p < ND / 2; ++p) {
-          const double2 d2 = lds_f64x2(vd_a + doff + 16 * p);
-          w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
-          w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+          const double2 v2 = lds_f64x2(vd_a + doff + 16 * p);
+          Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+          Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
         }
       }
-      double w = w0 + w1;
-      if (SPLIT) w += __shfl_xor_sync(WBC_FULL_MASK, w, 16);
-      const double z = z0 + z1, dd2 = e0 + e1;
-      // r = R^-1 d1 on the inequality block [p_eq, iq)
-      double rr = (lane < iq) ? sgn * d_own : 0.0;
-#pragma unroll 1
-      for (int k = iq - 1; k >= p_eq; --k) {
-        const int slot_k = __shfl_sync(WBC_FULL_MASK, slot, k);
-        const double rk = __shfl_sync(WBC_FULL_MASK, rr * rinv, k);
-        if (lane == k) rr = rk;
-        else if (lane < k && lane >= p_eq) rr -= lds_f64(R_a + 8 * (lane * LD + slot_k)) * rk;
+      if (!is_eq) {                                                   // R column (signed): [d1 ; -sigma]
+        const int slot_new = __shfl_sync(WBC_FULL_MASK, slot, iq);
+        if (lane < iq) sts_f64(R_a + 8 * (lane * LD + slot_new), sgn * d_own);
+        if (lane == iq) sts_f64(R_a + 8 * (iq * LD + slot_new), -sgn * sigma);
       }
-      // constraint value at x:  s = n.x - bnd  (negative when violated)
-      double s_ip;
-      {
-        const double v_i = __shfl_sync(WBC_FULL_MASK, is_box ? x : ax, owner);
-        const double lo_i = __shfl_sync(WBC_FULL_MASK, is_box ? lb : clb, owner);
-        const double up_i = __shfl_sync(WBC_FULL_MASK, is_box ? ub : cub, owner);
-        s_ip = (side > 0) ? (up_i - v_i) : (v_i - lo_i);
+      if (lane == iq) {
+        rinv = -sgn * isig;                                           // 1 / R_iq,iq
+        ws_c = ip;
+        u = u_new;
       }
-      const bool dependent = dd2 <= WBC_QP_DEP_TOL * dd;
-
-      if (is_eq) {
-        if (dependent) {                                             // redundant (or inconsistent) equality
-          if (fabs(s_ip) > 1e-8) res.status |= WBC_QP_INFEASIBLE;
-          break;
-        }
-        const double t = -s_ip / dd2;
-        x = fma(t * sgn, z, x);
-        ax = fma(t * sgn, w, ax);
-        u_new = t;
-      } else {
-        // dual step length over active inequalities
-        double t1 = INFINITY;
-        int l = 0x7fffffff;
-        if (lane >= p_eq && lane < iq && rr > 0.0) { t1 = u / rr; l = lane; }
-        warp_argmin(t1, l);
-        const double t2 = dependent ? INFINITY : -s_ip / dd2;
-        const double t = fmin(t1, t2);
-        if (!(t < INFINITY)) { res.status |= WBC_QP_INFEASIBLE; done = true; break; }
-        if (lane >= p_eq && lane < iq) u -= t * rr;
-        u_new += t;
-        if (!dependent) {
-          x = fma(t * sgn, z, x);
-          ax = fma(t * sgn, w, ax);
-        }
-        if (dependent || !(t2 <= t1)) {
-          // ---------------------------------------------------- drop working-set position l
-          const int c_drop = __shfl_sync(WBC_FULL_MASK, ws_c, l);
-#pragma unroll 1
-          for (int k = l; k < iq - 1; ++k) {
-            const int slot_k1 = __shfl_sync(WBC_FULL_MASK, slot, k + 1);
-            const double a = lds_f64(R_a + 8 * (k * LD + slot_k1)), b = lds_f64(R_a + 8 * ((k + 1) * LD + slot_k1));
-            const double rho = sqrt(a * a + b * b);
-            const double cg = (rho > 0.0) ? a / rho : 1.0, sg = (rho > 0.0) ? b / rho : 0.0;
-            __syncwarp();                                             // everyone has read a, b before rows k, k+1 change
-            if (lane > k && lane < iq) {
-              const uint32_t a0 = R_a + 8 * (k * LD + slot), a1 = R_a + 8 * ((k + 1) * LD + slot);
-              const double r0 = lds_f64(a0), r1 = lds_f64(a1);
-              sts_f64(a0, cg * r0 + sg * r1);
-              sts_f64(a1, -sg * r0 + cg * r1);
-            }
-            // rotate columns k, k + 1 of J and of the rows' d vectors
-            switch (k) {
-#define WBC_GV(j) case (j): if ((j) + 1 < NV) { \
-                const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)]; \
-                Jr[WBC_IX(j)] = cg * j0 + sg * j1; Jr[WBC_IX((j) + 1)] = -sg * j0 + cg * j1; \
-                if (!SPLIT || (j) + 1 < HALF) { \
-                  if (!upper) { const double d0 = Dr[WBC_DX(j)], d1 = Dr[WBC_DX((j) + 1)]; \
-                    Dr[WBC_DX(j)] = cg * d0 + sg * d1; Dr[WBC_DX((j) + 1)] = -sg * d0 + cg * d1; } \
-                } else if ((j) >= HALF) { \
-                  if (upper) { const double d0 = Dr[WBC_DX((j) - HALF)], d1 = Dr[WBC_DX((j) + 1 - HALF)]; \
-                    Dr[WBC_DX((j) - HALF)] = cg * d0 + sg * d1; Dr[WBC_DX((j) + 1 - HALF)] = -sg * d0 + cg * d1; } \
-                } else {   /* j == HALF - 1: column j sits in the lower lane, column j + 1 in the upper lane */ \
-                  const double mine = upper ? Dr[0] : Dr[WBC_DX(HALF - 1)]; \
-                  const double other = __shfl_xor_sync(WBC_FULL_MASK, mine, 16); \
-                  if (upper) Dr[0] = -sg * other + cg * mine; else Dr[WBC_DX(HALF - 1)] = cg * mine + sg * other; \
-                } } break;
-              WBC_REP32_ASC(WBC_GV)
-#undef WBC_GV
-              default: break;
-            }
-            __syncwarp();
-          }
-          {
-            const int dropped_slot = __shfl_sync(WBC_FULL_MASK, slot, l);
-            const int nc_ = __shfl_down_sync(WBC_FULL_MASK, ws_c, 1);
-            const int nslot = __shfl_down_sync(WBC_FULL_MASK, slot, 1);
-            const double nu = __shfl_down_sync(WBC_FULL_MASK, u, 1);
-            if (lane >= l && lane < iq - 1) { ws_c = nc_; slot = nslot; u = nu; }
-            if (lane == iq - 1) { slot = dropped_slot; ws_c = -1; u = 0.0; }
-            if (lane >= l && lane < iq - 1) rinv = 1.0 / lds_f64(R_a + 8 * (lane * LD + slot));
-            if (c_drop < n) { if (lane == c_drop) bstat = 0; }
-            else if (lane == c_drop - n) cstat = 0;
-            iq--;
-          }
-          __syncwarp();
-          continue;                                                   // retry the same candidate
-        }
-      }
-      // -------------------------------------------------------- full step: constraint ip enters at position iq
-      {
-        const double d_iq = __shfl_sync(WBC_FULL_MASK, d_own, iq);    // unsigned
-        const double nrm = sqrt(dd2);
-        const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
-        const double v_iq = d_iq + sigma;
-        const double beta = 1.0 / (sigma * v_iq);
-        double jiq = 0.0, diq = 0.0;
-        switch (iq) {                                                 // column iq of J and of the rows' d vectors
-#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; \
-            if (!SPLIT) diq = Dr[WBC_DX(j)]; \
-            else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
-            else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
-          WBC_REP32_ASC(WBC_PK)
-#undef WBC_PK
-          default: break;
-        }
-        if (SPLIT) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
-        const double nbJ = -beta * fma(sigma, jiq, z);
-        const double nbD = -beta * fma(sigma, diq, w);
-        if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);                  // vd = v = d2 + sigma e_iq (zeros below iq)
-        __syncwarp();
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          const double2 v2 = lds_f64x2(vd_a + 16 * p);
-          Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
-          if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
-          if (2 * p + 1 < NV) {
-            Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
-            if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
-          }
-        }
-        if (SPLIT) {
-#pragma unroll
-          for (int p = 0; p < ND / 2; ++p) {
-            const double2 v2 = lds_f64x2(vd_a + doff + 16 * p);
-            Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
-            Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
-          }
-        }
-        if (!is_eq) {                                                 // R column (signed): [d1 ; -sigma]
-          const int slot_new = __shfl_sync(WBC_FULL_MASK, slot, iq);
-          if (lane < iq) sts_f64(R_a + 8 * (lane * LD + slot_new), sgn * d_own);
-          if (lane == iq) sts_f64(R_a + 8 * (iq * LD + slot_new), -sgn * sigma);
-        }
-        if (lane == iq) {
-          rinv = -1.0 / (sgn * sigma);
-          ws_c = ip;
-          u = u_new;
-        }
-        const int st = is_eq ? 3 : (side > 0 ? 2 : 1);
-        if (is_box) { if (lane == ip) bstat = st; }
-        else if (lane == owner) cstat = st;
-        iq++;
-        if (is_eq) p_eq = iq;
-        __syncwarp();
-      }
-      break;
+      const int st = is_eq ? 3 : (side > 0 ? 2 : 1);
+      if (is_box) { if (lane == ip) bstat = st; }
+      else if (lane == owner) cstat = st;
+      iq++;
+      if (is_eq) p_eq = iq;
+      have = false;
     }
     __syncwarp();
   }

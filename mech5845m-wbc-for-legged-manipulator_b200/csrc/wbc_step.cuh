@@ -248,7 +248,10 @@ template <int NV, bool DEBUG_OUT, bool SPLIT>
 __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevModel* __restrict__ M,
                                               double* __restrict__ ws, const StepLayout L, long long sidx,
                                               const bool valid) {
-  constexpr bool PS = !DEBUG_OUT;
+#ifndef WBC_PHASE_SYNC
+#define WBC_PHASE_SYNC 1
+#endif
+  constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
   constexpr int LD = NV | 1;
   const int lane = threadIdx.x & 31;
   const WbcConfig& cfg = P.cfg;
