@@ -32,6 +32,8 @@ struct DevModel {
   uint32_t sub_joints[WBC_MAX_NV];       // bit j: joint j is in the subtree moved by column k
   int32_t frame_parent[WBC_MAX_FRAMES];
   uint32_t frame_supp[WBC_MAX_FRAMES];
+  int32_t pl_ident[WBC_MAX_JOINTS];      // 1: the joint placement has an identity rotation (pure translation)
+  int32_t fr_ident[WBC_MAX_FRAMES];      // 1: the frame offset has an identity rotation
   double plR[WBC_MAX_JOINTS][9];
   double plp[WBC_MAX_JOINTS][3];
   double axis[WBC_MAX_JOINTS][3];
@@ -71,6 +73,18 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void lds_vec3(uint32_t a, double* v) {
+  v[0] = lds_f64(a); v[1] = lds_f64(a + 8); v[2] = lds_f64(a + 16);
+}
+__device__ __forceinline__ void lds_mat3(uint32_t a, double* R) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = lds_f64(a + 8 * i);
 }
 __device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");

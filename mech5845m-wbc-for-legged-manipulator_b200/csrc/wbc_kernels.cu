@@ -60,16 +60,8 @@ __global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>
   stage_model(P.model, Ms);
   const StepLayout L = step_layout(NV, P.nC);
   const int warp = threadIdx.x >> 5;
-  const int wpc = blockDim.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
-  for (long long base = (long long)blockIdx.x * wpc; base < P.N; base += (long long)gridDim.x * wpc) {
-    long long s = base + warp;
-    const bool valid = s < P.N;          // padding warps shadow the last state so that block barriers stay uniform
-    if (!valid) s = P.N - 1;
-    if (DEBUG_OUT && !valid) continue;
-    warp_wbc_step<NV, DEBUG_OUT, SPLIT>(P, Ms, ws, L, s, valid);
-    __syncwarp();
-  }
+  warp_wbc_states<NV, DEBUG_OUT, SPLIT>(P, Ms, ws, L);
 }
 
 // FK + frame Jacobians accessor (HBM-write bound): one state per warp
@@ -320,7 +312,7 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
     const double hdiag = (lane < n) ? Hrow[lane] : 0.0;
     __syncwarp();
     QpRegShared S;
-    S.R = Hs; S.col = col; S.vd = vd; S.C = Cs;
+    S.R = smem_addr(Hs); S.col = smem_addr(col); S.vd = smem_addr(vd); S.C = smem_addr(Cs);
     double x;
     const QpResult res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
     if (lane < n) P.x[s * n + lane] = x;
@@ -385,6 +377,10 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
       if (m->depth[j] > maxd) maxd = m->depth[j];
     }
     memcpy(m->plR[j], t->placement_R[j], sizeof(double) * 9);
+    {
+      static const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      m->pl_ident[j] = memcmp(t->placement_R[j], I3, sizeof(I3)) == 0;
+    }
     memcpy(m->plp[j], t->placement_p[j], sizeof(double) * 3);
     memcpy(m->axis[j], t->axis[j], sizeof(double) * 3);
     m->mass[j] = t->mass[j];
@@ -423,6 +419,10 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
     m->frame_parent[f] = t->frame_parent[f];
     m->frame_supp[f] = m->joint_supp[t->frame_parent[f]];
     memcpy(m->frR[f], t->frame_R[f], sizeof(double) * 9);
+    {
+      static const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      m->fr_ident[f] = memcmp(t->frame_R[f], I3, sizeof(I3)) == 0;
+    }
     memcpy(m->frp[f], t->frame_p[f], sizeof(double) * 3);
   }
   memcpy(m->lower, t->lower, sizeof(double) * WBC_MAX_NQ);
@@ -493,7 +493,16 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   memset(&P->dbg, 0, sizeof(P->dbg));
   P->nC = cfg_nc(*cfg);
   P->m_rows = cfg_m(*cfg, model->host.nv);
-  P->flags = (int)io->flags;
+  P->flags = (int)io->flags & ~WBC_STEP_FLAG_WEIGHTS_IDENTITY;
+  {
+    bool ident = true;
+    for (int t = 0; t < 6 && ident; ++t) {
+      const double* W = (t < 5) ? cfg->ee_weight[t] : cfg->trunk_weight;
+      for (int k = 0; k < 36; ++k)
+        if (W[k] != ((k % 7 == 0) ? 1.0 : 0.0)) { ident = false; break; }
+    }
+    if (ident) P->flags |= WBC_STEP_FLAG_WEIGHTS_IDENTITY;   // W = I: W (J w) == J w exactly, skip the 6x6 products
+  }
   if (P->nC > WBC_MAX_NC) return fail(WBC_ERR_UNSUPPORTED, "more than 32 constraint rows%s");
   return WBC_OK;
 }

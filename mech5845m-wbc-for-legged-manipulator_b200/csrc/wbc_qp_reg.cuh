@@ -36,11 +36,11 @@
 #pragma once
 #include "wbc_qp.cuh"
 
-struct QpRegShared {
-  double* R;         // [NV][NV + 2]: columns of L during the factorisation, then R with LD = NV | 1
-  double* col;       // [64], 16-byte aligned: 1 / L_kk
-  double* vd;        // [32], 16-byte aligned: broadcast vector
-  const double* C;   // [nC][LD] constraint rows (read once)
+struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byte aligned
+  uint32_t R;        // [NV][NV + 2]: columns of L during the factorisation, then R with LD = NV | 1
+  uint32_t col;      // [64]: 1 / L_kk
+  uint32_t vd;       // [32]: broadcast vector
+  uint32_t C;        // [nC][LD] constraint rows (read once; up to two doubles past the end are touched)
 };
 
 // 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free
@@ -94,9 +94,9 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   const bool upper = SPLIT && lane >= 16;    // this lane holds the second half of its row's d vector
   const int crow = SPLIT ? (lane & 15) : lane;
   const bool has_row = crow < nC;
-  const uint32_t R_a = smem_addr(S.R);       // also the columns of L
-  const uint32_t vd_a = smem_addr(S.vd);
-  const uint32_t rk_a = smem_addr(S.col);
+  const uint32_t R_a = S.R;                  // also the columns of L
+  const uint32_t vd_a = S.vd;
+  const uint32_t rk_a = S.col;
   const uint32_t doff = upper ? 8u * HALF : 0u;   // byte offset of this lane's segment inside a broadcast vector
   QpResult res;
   res.status = 0;
@@ -155,7 +155,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   double Jr[NV], Dr[ND];
   double shift = 0.0;                                   // sum_k C[c][k] x_k over the fixed variables
   {
-    const uint32_t crow_a = smem_addr(S.C) + 8 * ((has_row ? crow : 0) * LD) + doff;
+    const uint32_t crow_a = S.C + 8 * ((has_row ? crow : 0) * LD) + doff;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const double gj = lds_f64(vd_a + 8 * j);

@@ -11,11 +11,15 @@
 #pragma once
 #include "wbc_qp_reg.cuh"
 
-#define WBC_IO_TARGETS 0
-#define WBC_IO_MEM 18
-#define WBC_IO_REF 90
-#define WBC_IO_TOTAL 114
+// per-state input block in shared memory (double-buffered: the next state's block is fetched with cp.async
+// while the QP of the current one runs)
+#define WBC_IN_Q 0          // q[nq <= 33]
+#define WBC_IN_TARGETS 34   // 18
+#define WBC_IN_MEM 52       // 72
+#define WBC_IN_REF 124      // 24
+#define WBC_IN_TOTAL 148
 #define WBC_HOT_FRAMES 6
+#define WBC_STEP_FLAG_WEIGHTS_IDENTITY 0x10000   // internal (set by the host wrapper): every 6x6 task weight is I
 
 // offsets inside mem / ref blocks
 #define MEM_PREV_EE_POS 0
@@ -27,10 +31,8 @@
 #define REF_INIT_TRUNK_POS 18
 #define REF_INIT_TRUNK_EUL 21
 
-
-
 struct StepLayout {   // per-warp shared-memory layout in doubles (every offset even: 16-byte aligned)
-  int hs, ast, col, omf, vec, io, total;
+  int hs, ast, col, omf, vec, in, total;
 };
 
 __host__ __device__ inline int wbc_ld(int nv) { return nv | 1; }
@@ -44,15 +46,15 @@ __host__ __device__ inline StepLayout step_layout(int nv, int nC) {
   if (r0 < fk) r0 = fk;
   r0 = (r0 + 1) & ~1;
   int r1 = nv * WBC_LDT;                               // transposed task rows AsT, later the constraint rows C
-  if (r1 < nC * ld) r1 = nC * ld;
+  if (r1 < nC * ld + 2) r1 = nC * ld + 2;
   r1 = (r1 + 1) & ~1;
   L.hs = 0;
   L.ast = r0;
   L.col = r0 + r1;
   L.omf = L.col + 64;
   L.vec = L.omf + WBC_HOT_FRAMES * WBC_T_STRIDE + 2;   // 6 * 13 + 2 = 80
-  L.io = L.vec + 40 + 32 + 32 + 32 + 40;               // qs[40] vd[32] clb[32] cub[32] bs[40]
-  L.total = L.io + WBC_IO_TOTAL + 2;
+  L.in = L.vec + 32 + 32 + 32 + 40;                    // vd[32] clb[32] cub[32] bs[40]
+  L.total = L.in + 2 * WBC_IN_TOTAL;
   L.total = (L.total + 1) & ~1;
   return L;
 }
@@ -129,90 +131,112 @@ __device__ __forceinline__ void integrate_freeflyer(const double* q, const doubl
   out[3] = rq[0] * al; out[4] = rq[1] * al; out[5] = rq[2] * al; out[6] = rq[3] * al;
 }
 
-// calcTargetVelEE3 (Robot_Wrapper4.py:1052-1157): lane i in 0..4.  Writes b (6) and updates the staged memory.
-__device__ __forceinline__ void ee_task_target(const WbcConfig& cfg, int i, const double* __restrict__ oMf,
-                                               double* __restrict__ io, double inv_dt, double* b) {
-  const double* target = io + WBC_IO_TARGETS + 3 * i;
-  double* prev = io + WBC_IO_MEM + MEM_PREV_EE_POS + 3 * i;
-  double* prevR = io + WBC_IO_MEM + MEM_PREV_EE_ROT + 9 * i;
-  const double* fk = oMf + i * WBC_T_STRIDE + 9;
-  double ref_vel[3], err[3], ge[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    ref_vel[k] = (target[k] - prev[k]) * inv_dt;
-    err[k] = (target[k] - fk[k]) * inv_dt;
-  }
-  mat3_vec(cfg.ee_gain_pos[i], err, ge);
-  double qref[4], Rref[9];
-  scipy_quat_from_euler_xyz(io + WBC_IO_REF + REF_DEF_EE_ORI + 3 * i, qref);
-  scipy_matrix_from_quat(qref, Rref);
-  double dR[9], sk[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) dR[k] = (Rref[k] - prevR[k]) * inv_dt;
-  mat3_mul_bt(dR, Rref, sk);                                   // (dR/dt) * Rref^T   (:1125)
-  const double wgt = cfg.cart_task_weight[i];
-  b[0] = (ref_vel[0] + ge[0]) * wgt;
-  b[1] = (ref_vel[1] + ge[1]) * wgt;
-  b[2] = (ref_vel[2] + ge[2]) * wgt;
-  b[3] = sk[7] * wgt;                                          // skew[2,1]
-  b[4] = sk[2] * wgt;                                          // skew[0,2]
-  b[5] = sk[3] * wgt;                                          // skew[1,0]
-#pragma unroll
-  for (int k = 0; k < 3; ++k) prev[k] = target[k];             // :1151
-#pragma unroll
-  for (int k = 0; k < 9; ++k) prevR[k] = Rref[k];              // :1152
+// 8-byte asynchronous global -> shared copy (LDGSTS); rows of q are only 8-byte aligned (nq is odd)
+__device__ __forceinline__ void cp_async8(uint32_t dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// fetch the input block of state s: q, targets, task memory, references (1128 B for nq = 27), coalesced
+template <int NV>
+__device__ __forceinline__ void prefetch_inputs(const WbcStepIO& io, long long s, uint32_t in_a, int lane) {
+  constexpr int nq = NV + 1;
+  const double* qg = io.q + s * nq;
+  if (lane < nq) cp_async8(in_a + 8 * (WBC_IN_Q + lane), qg + lane);
+  if (nq > 32 && lane == 0) cp_async8(in_a + 8 * (WBC_IN_Q + 32), qg + 32);
+  const double* tg = io.targets + s * WBC_TARGETS_STRIDE;
+  if (lane < WBC_TARGETS_STRIDE) cp_async8(in_a + 8 * (WBC_IN_TARGETS + lane), tg + lane);
+  const double* mg = io.mem_in + s * WBC_MEM_STRIDE;
+  cp_async8(in_a + 8 * (WBC_IN_MEM + lane), mg + lane);
+  cp_async8(in_a + 8 * (WBC_IN_MEM + 32 + lane), mg + 32 + lane);
+  if (lane < WBC_MEM_STRIDE - 64) cp_async8(in_a + 8 * (WBC_IN_MEM + 64 + lane), mg + 64 + lane);
+  const double* rg = io.ref + s * WBC_REF_STRIDE;
+  if (lane < WBC_REF_STRIDE) cp_async8(in_a + 8 * (WBC_IN_REF + lane), rg + lane);
+  cp_async_commit();
 }
 
-// calcTargetVelTrunk2 (Robot_Wrapper4.py:948-1015): one lane.
-__device__ __forceinline__ void trunk_task_target(const WbcConfig& cfg, const double* __restrict__ oMf,
-                                                  const double* fkq, double* __restrict__ io, double inv_dt, double* b) {
-  const double* target = io + WBC_IO_TARGETS + 15;
-  double* prev = io + WBC_IO_MEM + MEM_PREV_TRUNK_REF;
-  double* oldR = io + WBC_IO_MEM + MEM_OLD_TRUNK_ROT;
-  const double* fk = oMf + WBC_FRAME_TRUNK * WBC_T_STRIDE + 9;
-  double ref_vel[3], err[3], ge[3];
+#define WBC_MOFF(f) ((uint32_t)offsetof(DevModel, f))
+
+// forwardKinematics into shared memory (stride WBC_T_STRIDE), level by level; 32-bit shared addressing.
+__device__ __forceinline__ void warp_fk_a(uint32_t M_a, uint32_t q_a, uint32_t oMi_a, int lane) {
+  double Rl[9], pl[3];
+  int myDepth = 0, par = 0;
+  const int nj = lds_s32(M_a + WBC_MOFF(njoints));
+  const bool active = lane >= 1 && lane < nj;
+  if (active) {
+    const int jt = lds_s32(M_a + WBC_MOFF(jtype) + 4 * lane);
+    const int iq = lds_s32(M_a + WBC_MOFF(idx_q) + 4 * lane);
+    par = lds_s32(M_a + WBC_MOFF(parent) + 4 * lane);
+    myDepth = lds_s32(M_a + WBC_MOFF(depth) + 4 * lane);
+    const bool ident = lds_s32(M_a + WBC_MOFF(pl_ident) + 4 * lane) != 0;
+    const uint32_t qa = q_a + 8 * iq;
+    double Rj[9], pj[3] = {0.0, 0.0, 0.0}, plp[3];
+    lds_vec3(M_a + WBC_MOFF(plp) + 24 * lane, plp);
+    if (jt == WBC_JT_FREEFLYER) {
+      quat_to_matrix_eigen(lds_f64(qa + 24), lds_f64(qa + 32), lds_f64(qa + 40), lds_f64(qa + 48), Rj);
+      lds_vec3(qa, pj);
+    } else {
+      double ax[3];
+      lds_vec3(M_a + WBC_MOFF(axis) + 24 * lane, ax);
+      const double qv = lds_f64(qa);
+      if (jt == WBC_JT_REVOLUTE) {
+        double sn, cs;
+        sincos(qv, &sn, &cs);
+        axis_angle_matrix(ax, sn, cs, Rj);
+      } else {  // prismatic
+        Rj[0] = 1; Rj[1] = 0; Rj[2] = 0; Rj[3] = 0; Rj[4] = 1; Rj[5] = 0; Rj[6] = 0; Rj[7] = 0; Rj[8] = 1;
+        pj[0] = ax[0] * qv; pj[1] = ax[1] * qv; pj[2] = ax[2] * qv;
+      }
+    }
+    if (ident) {                       // pure-translation placement: I * Rj and I * pj are exact, skip them
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    ref_vel[k] = (target[k] - prev[k]) * inv_dt;
-    err[k] = (target[k] - fk[k]) * inv_dt;
+      for (int i = 0; i < 9; ++i) Rl[i] = Rj[i];
+      pl[0] = pj[0]; pl[1] = pj[1]; pl[2] = pj[2];
+    } else {
+      double PR[9];
+      lds_mat3(M_a + WBC_MOFF(plR) + 72 * lane, PR);
+      mat3_mul(PR, Rj, Rl);
+      mat3_vec(PR, pj, pl);
+    }
+    if (jt == WBC_JT_REVOLUTE) { pl[0] = plp[0]; pl[1] = plp[1]; pl[2] = plp[2]; }   // (placement * 0 + p, exactly p)
+    else { pl[0] += plp[0]; pl[1] += plp[1]; pl[2] += plp[2]; }
   }
-  mat3_vec(cfg.trunk_gain_pos, err, ge);
-  double r[4], Rref[9];
-  scipy_quat_from_euler_xyz(io + WBC_IO_REF + REF_DEF_TRUNK_ORI, r);
-  scipy_matrix_from_quat(r, Rref);
-  const double* f = fkq;
-  double qe[3];
-  qe[0] = (f[3] * r[0]) - (f[0] * r[3]) + (f[1] * r[2]) - (f[2] * r[1]);
-  qe[1] = (f[3] * r[1]) - (f[1] * r[3]) - (f[0] * r[2]) + (f[2] * r[0]);
-  qe[2] = (f[0] * r[1]) - (f[1] * r[0]);                       // :976 -- the w*z terms cancel exactly
-  double dR[9], sk[9];
+  const int maxdepth = lds_s32(M_a + WBC_MOFF(maxdepth));
+  const uint32_t out_a = oMi_a + 8 * WBC_T_STRIDE * lane;
+  for (int d = 1; d <= maxdepth; ++d) {
+    if (active && myDepth == d) {
+      if (par == 0) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) dR[k] = (Rref[k] - oldR[k]) * inv_dt;
-  mat3_mul(dR, Rref, sk);                                      // (dR/dt) * Rref, NOT transposed (:984)
-  const double wgt = cfg.cart_task_weight[5];
-  b[0] = (ref_vel[0] + ge[0]) * wgt;
-  b[1] = (ref_vel[1] + ge[1]) * wgt;
-  b[2] = (ref_vel[2] + ge[2]) * wgt;
-  b[3] = (sk[7] + cfg.trunk_gain_ori[0] * qe[0]) * wgt;
-  b[4] = (sk[2] + cfg.trunk_gain_ori[1] * qe[1]) * wgt;
-  b[5] = (sk[3] + cfg.trunk_gain_ori[2] * qe[2]) * wgt;
+        for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, Rl[i]);
+        sts_f64(out_a + 72, pl[0]); sts_f64(out_a + 80, pl[1]); sts_f64(out_a + 88, pl[2]);
+      } else {
+        const uint32_t pa = oMi_a + 8 * WBC_T_STRIDE * par;
+        double Rp[9], R[9], p[3], pp[3];
+        lds_mat3(pa, Rp);
+        lds_vec3(pa + 72, pp);
+        mat3_mul(Rp, Rl, R);
+        mat3_vec(Rp, pl, p);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) prev[k] = target[k];             // :995
-#pragma unroll
-  for (int k = 0; k < 9; ++k) oldR[k] = Rref[k];               // :996
+        for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, R[i]);
+        sts_f64(out_a + 72, p[0] + pp[0]); sts_f64(out_a + 80, p[1] + pp[1]); sts_f64(out_a + 88, p[2] + pp[2]);
+      }
+    }
+    __syncwarp();
+  }
 }
 
 // velDamperJointConstraints (Robot_Wrapper4.py:572-637) for velocity index k.
-__device__ __forceinline__ void damper_bounds(const DevModel* __restrict__ M, const WbcConfig& cfg,
-                                              const double* __restrict__ qs, int k, double& lbv, double& ubv) {
+__device__ __forceinline__ void damper_bounds_a(uint32_t M_a, const WbcConfig& cfg, uint32_t q_a, int k, double& lbv,
+                                                double& ubv) {
   const int grip = cfg.gripper_joint_id;
   const int qidx = (k < 6) ? k : k + 1;                        // np.delete(., 6)
   double lo, up;
   if (qidx < 7) { lo = -5.0; up = 5.0; }
   else if (qidx >= grip - 2 + 7) { lo = 0.0; up = 0.0; }
-  else { lo = M->lower[qidx]; up = M->upper[qidx]; }
-  const double vel = (k < 7) ? 5.0 : M->velocity[k];           // vel_lim[i] = 5 for i < 7 (:593)
-  const double c = (cfg.compat_flags & WBC_COMPAT_DAMPER_OFF_BY_ONE) ? qs[k] : qs[qidx];   // quirk D.2
+  else { lo = lds_f64(M_a + WBC_MOFF(lower) + 8 * qidx); up = lds_f64(M_a + WBC_MOFF(upper) + 8 * qidx); }
+  const double vel = (k < 7) ? 5.0 : lds_f64(M_a + WBC_MOFF(velocity) + 8 * k);   // vel_lim[i] = 5 for i < 7 (:593)
+  const double c = lds_f64(q_a + 8 * ((cfg.compat_flags & WBC_COMPAT_DAMPER_OFF_BY_ONE) ? k : qidx));   // quirk D.2
   const double coef = cfg.damper_coef, qi = cfg.damper_qi, qsv = cfg.damper_qs;
   if (c <= lo + qi) {
     lbv = -coef * (c - lo - qsv) / (qi - qsv);
@@ -233,151 +257,62 @@ __device__ __forceinline__ void damper_bounds(const DevModel* __restrict__ M, co
   if (k >= grip - 2 + 6) { lbv = 0.0; ubv = 0.0; }
 }
 
-// One WBC tick for the state `sidx`, executed by one warp.  ws: this warp's shared workspace.
-// The warps of a CTA are re-aligned with a block barrier at the phase boundaries (PHASE_SYNC): the tick is
-// ~10^4 mostly straight-line instructions, far more than the instruction cache holds, so warps that drift apart
-// each stream the whole code through the cache on their own (ncu: 50 % of stall samples were `no_instruction`);
-// in step, one fetch feeds all warps.  `valid` == false: a padding warp that shadows the last state, no writes.
+// getFrameJacobian column from the WORLD joint-Jacobian column S for a frame at position p (LOCAL_WORLD_ALIGNED)
+// or as is (WORLD); zero outside the support.
+__device__ __forceinline__ void frame_jac_lwa(const double* S, bool sup, const double* p, bool world, double* Jc) {
+  if (!sup) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Jc[i] = 0.0;
+    return;
+  }
+  if (world) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Jc[i] = S[i];
+    return;
+  }
+  double pxw[3];
+  cross3(p, S + 3, pxw);
+  Jc[0] = S[0] - pxw[0]; Jc[1] = S[1] - pxw[1]; Jc[2] = S[2] - pxw[2];
+  Jc[3] = S[3]; Jc[4] = S[4]; Jc[5] = S[5];
+}
+
 template <bool ON>
 __device__ __forceinline__ void phase_sync() {
   if (ON) __syncthreads();
   else __syncwarp();
 }
 
-template <int NV, bool DEBUG_OUT, bool SPLIT>
-__device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevModel* __restrict__ M,
-                                              double* __restrict__ ws, const StepLayout L, long long sidx,
-                                              const bool valid) {
 #ifndef WBC_PHASE_SYNC
 #define WBC_PHASE_SYNC 1
 #endif
+
+// All WBC ticks of one warp: states first, first + stride, ...  `ws`: this warp's shared workspace.
+// The warps of a CTA are re-aligned with a block barrier at the phase boundaries (PHASE_SYNC): the tick is
+// ~10^4 mostly straight-line instructions, far more than the 32 KB instruction cache holds, so warps that drift
+// apart each stream the whole code from L2 on their own (measured: 2.4x slower without the barriers); in step,
+// one fetch feeds all warps.  Padding warps shadow the last state (no writes) so the barriers stay uniform.
+// Shared memory is addressed through 32-bit shared-window addresses (wbc_device.cuh: smem_addr, lds_*, sts_*).
+template <int NV, bool DEBUG_OUT, bool SPLIT>
+__device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws, const StepLayout L) {
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
   constexpr int LD = NV | 1;
+  constexpr int nq = NV + 1;
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const WbcConfig& cfg = P.cfg;
-  const int nq = NV + 1;
   const double dt = P.io.dt;
   const double inv_dt = 1.0 / dt;       // the reference divides by dt; multiplying by 1/dt differs by <= 1 ulp
-  double* Hs = ws + L.hs;           // [NV][LD] rows of H; the QP reuses it for its R factor
-  double* AsT = ws + L.ast;         // [NV][WBC_LDT] column k of the Cartesian task rows (36 values)
-  double* Cs = ws + L.ast;          // [nC][LD] constraint rows (after AsT is dead)
-  double* oMi = ws + L.hs;
-  double* oMf = ws + L.omf;
-  double* qs = ws + L.vec;          // [40]
-  double* vd = qs + 40;             // [32]
-  double* clbs = vd + 32;
-  double* cubs = clbs + 32;
-  double* bs = cubs + 32;           // [40]
-  double* io = ws + L.io;
+  const uint32_t M_a = smem_addr(Ms);
+  const uint32_t ws_a = smem_addr(ws);
+  const uint32_t hs_a = ws_a + 8 * L.hs;      // [NV][LD] rows of H; then the QP's L columns / R factor; oMi scratch before
+  const uint32_t ast_a = ws_a + 8 * L.ast;    // [NV][WBC_LDT] transposed task rows; then [nC][LD] constraint rows
+  const uint32_t omi_a = hs_a;
+  const uint32_t omf_a = ws_a + 8 * L.omf;
+  const uint32_t vd_a = ws_a + 8 * L.vec;
+  const uint32_t clb_a = vd_a + 8 * 32, cub_a = clb_a + 8 * 32, bs_a = cub_a + 8 * 32;
+  const uint32_t in0_a = ws_a + 8 * L.in;
 
-  // ---------------------------------------------------------------- stage inputs (coalesced)
-  {
-    const double* qg = P.io.q + sidx * nq;
-    for (int i = lane; i < nq; i += 32) qs[i] = qg[i];
-    const double* tg = P.io.targets + sidx * WBC_TARGETS_STRIDE;
-    if (lane < WBC_TARGETS_STRIDE) io[WBC_IO_TARGETS + lane] = tg[lane];
-    const double* mg = P.io.mem_in + sidx * WBC_MEM_STRIDE;
-    for (int i = lane; i < WBC_MEM_STRIDE; i += 32) io[WBC_IO_MEM + i] = mg[i];
-    const double* rg = P.io.ref + sidx * WBC_REF_STRIDE;
-    if (lane < WBC_REF_STRIDE) io[WBC_IO_REF + lane] = rg[lane];
-  }
-  phase_sync<PS>();
-
-  // ---------------------------------------------------------------- kinematics
-  warp_fk(M, qs, oMi, lane);
-  double Sc[6];
-  warp_jac_column(M, oMi, lane, Sc);
-  if (lane < WBC_HOT_FRAMES) {       // hot frames: 5 EE + trunk
-    const int par = M->frame_parent[lane];
-    const double* Pm = oMi + par * WBC_T_STRIDE;
-    double Rp[9], R[9], p[3];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Rp[i] = Pm[i];
-    mat3_mul(Rp, M->frR[lane], R);
-    mat3_vec(Rp, M->frp[lane], p);
-    double* out = oMf + lane * WBC_T_STRIDE;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) out[i] = R[i];
-    out[9] = p[0] + Pm[9]; out[10] = p[1] + Pm[10]; out[11] = p[2] + Pm[11];
-  }
-  // centre of mass (only when the CoM constraint is on): lane j -> m_j * c_j in the world
-  double com_w[3] = {0, 0, 0};
-  double Jcom[2] = {0, 0};
-  if (cfg.constraint_mask & WBC_CON_COM) {
-    double mc[4] = {0, 0, 0, 0};
-    if (lane >= 1 && lane < M->njoints) {
-      const double* T = oMi + lane * WBC_T_STRIDE;
-      double R[9], c[3];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) R[i] = T[i];
-      mat3_vec(R, M->com[lane], c);
-      const double m = M->mass[lane];
-      mc[0] = m; mc[1] = m * (c[0] + T[9]); mc[2] = m * (c[1] + T[10]); mc[3] = m * (c[2] + T[11]);
-    }
-    // subtree sums for my column: sum over joints j in sub_joints[lane]
-    double sm = 0, s1 = 0, s2 = 0, s3 = 0;
-    const uint32_t sub = (lane < NV) ? M->sub_joints[lane] : 0u;
-    for (int j = 1; j < M->njoints; ++j) {
-      const double m0 = __shfl_sync(WBC_FULL_MASK, mc[0], j), m1 = __shfl_sync(WBC_FULL_MASK, mc[1], j);
-      const double m2 = __shfl_sync(WBC_FULL_MASK, mc[2], j), m3 = __shfl_sync(WBC_FULL_MASK, mc[3], j);
-      if ((sub >> j) & 1u) { sm += m0; s1 += m1; s2 += m2; s3 += m3; }
-    }
-    const double Mt = M->total_mass;
-    com_w[0] = warp_sum(mc[1]) / Mt; com_w[1] = warp_sum(mc[2]) / Mt; com_w[2] = warp_sum(mc[3]) / Mt;
-    // Jcom column = (sm * lin - (sum m c) x ang) / M   (only x, y rows are used, :670)
-    const double msc[3] = {s1, s2, s3};
-    double cx[3];
-    cross3(msc, Sc + 3, cx);
-    Jcom[0] = (sm * Sc[0] - cx[0]) / Mt;
-    Jcom[1] = (sm * Sc[1] - cx[1]) / Mt;
-  }
-  phase_sync<PS>();
-
-  // ---------------------------------------------------------------- task rows for my column (registers)
-  double a[36];
-#pragma unroll
-  for (int t = 0; t < 6; ++t) {
-    const bool on = (cfg.task_mask >> t) & 1;
-    double Jc[6];
-    if (on) {
-      // EE tasks: LOCAL_WORLD_ALIGNED (:476-480); trunk task: WORLD (:488)
-      frame_jac_column(Sc, M->frame_supp[t], lane, oMf + t * WBC_T_STRIDE,
-                       t < 5 ? WBC_RF_LOCAL_WORLD_ALIGNED : WBC_RF_WORLD, Jc);
-      const double w = cfg.cart_task_weight[t];
-      const double* W = (t < 5) ? cfg.ee_weight[t] : cfg.trunk_weight;
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        double s = 0.0;
-        if (t < 5) {                                             // A = W (J w)          (:480-482)
-#pragma unroll
-          for (int c = 0; c < 6; ++c) s += W[6 * r + c] * (Jc[c] * w);
-        } else {                                                 // A = (W J) w          (:488-490)
-#pragma unroll
-          for (int c = 0; c < 6; ++c) s += W[6 * r + c] * Jc[c];
-          s *= w;
-        }
-        a[6 * t + r] = s;
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 6; ++r) a[6 * t + r] = 0.0;
-    }
-  }
-
-  // ---------------------------------------------------------------- targets b (lanes 0..5), constraint bounds
-  double fkq[4] = {0, 0, 0, 1};
-  if (lane == 5) scipy_quat_from_matrix(oMf + WBC_FRAME_TRUNK * WBC_T_STRIDE, fkq);
-  if (lane < 6 && ((cfg.task_mask >> lane) & 1)) {
-    double b6[6];
-    if (lane < 5) ee_task_target(cfg, lane, oMf, io, inv_dt, b6);
-    else trunk_task_target(cfg, oMf, fkq, io, inv_dt, b6);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) bs[6 * lane + r] = b6[r];
-  } else if (lane < 6) {
-#pragma unroll
-    for (int r = 0; r < 6; ++r) bs[6 * lane + r] = 0.0;
-  }
-  // row layout of C
+  // row layout of C (uniform over the launch)
   int row_com = -1, row_trunk = -1, row_ee[5], nrows = 0;
   if (cfg.constraint_mask & WBC_CON_COM) { row_com = nrows; nrows += 2; }
   if (cfg.constraint_mask & WBC_CON_TRUNK) { row_trunk = nrows; nrows += 4; }
@@ -388,248 +323,472 @@ __device__ __forceinline__ void warp_wbc_step(const StepParams& P, const DevMode
   }
   const int row_extra = nrows;
   const int nC = nrows + cfg.n_extra_rows;
-  if (lane < 32) { clbs[lane] = 0.0; cubs[lane] = 0.0; }
-  __syncwarp();
-  if (row_trunk >= 0 && lane == 5) {                             // trunkConstraint (:707-754)
-    double eul[3];
-    scipy_euler_xyz_from_quat(fkq, eul);
-    const double* ip = io + WBC_IO_REF + REF_INIT_TRUNK_POS;
-    const double* ie = io + WBC_IO_REF + REF_INIT_TRUNK_EUL;
-    const double cur[4] = {oMf[WBC_FRAME_TRUNK * WBC_T_STRIDE + 11], eul[0], eul[1], eul[2]};
-    const double z_var = ip[2] * 0.25;
-    const double var = 1.5 * 0.1;
-    const double lo[4] = {ip[2] - z_var, ie[0] - var, ie[1] - var, ie[2] - var};
-    const double up[4] = {ip[2] + z_var, ie[0] + var, ie[1] + var, ie[2] + var};
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      clbs[row_trunk + r] = ((lo[r] - cur[r]) * inv_dt) * 0.5;
-      cubs[row_trunk + r] = ((up[r] - cur[r]) * inv_dt) * 0.5;
-    }
-  }
-  if (row_com >= 0 && lane == 0) {                               // CoMConstraint (:669-694)
-    const double* FL = oMf + 1 * WBC_T_STRIDE + 9;
-    const double* RR = oMf + 2 * WBC_T_STRIDE + 9;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      clbs[row_com + r] = ((RR[r] - com_w[r]) * inv_dt) * 0.8;
-      cubs[row_com + r] = ((FL[r] - com_w[r]) * inv_dt) * 0.8;
-    }
-  }
-  if (lane < cfg.n_extra_rows) {
-    clbs[row_extra + lane] = cfg.extra_lo[lane];
-    cubs[row_extra + lane] = cfg.extra_hi[lane];
-  }
-
-  // ---------------------------------------------------------------- box bounds, joint task
-  double lbv = 0.0, ubv = 0.0;
-  if (lane < NV) damper_bounds(M, cfg, qs, lane, lbv, ubv);
   const bool joint_on = (cfg.task_mask & WBC_TASK_JOINT) != 0;
   const double aj = joint_on ? (1.0 / NV) * cfg.joint_task_weight : 0.0;       // qpJointA (:1199-1206)
-  double bj = 0.0;
-  if (joint_on && cfg.joint_mode == WBC_JOINT_PREV && lane < NV)               // qpJointb "PREV" (:1216-1217)
-    bj = ((1.0 / NV) * qs[(lane < 6) ? lane : lane + 1]) * cfg.joint_task_weight;
+  const bool w_ident = (P.flags & WBC_STEP_FLAG_WEIGHTS_IDENTITY) != 0;        // every 6x6 task weight is the identity
 
-  // ---------------------------------------------------------------- H = A^T A, g = -A^T b
-  // Column `lane` of the 36 Cartesian rows goes to shared memory transposed (AsT[lane][r]); then for every
-  // (task t, supporting column l) pair lane i adds  sum_r A[6t+r][i] A[6t+r][l]  to H[i][l]: three 128-bit
-  // broadcast loads and six FMAs.  Pairs outside the frame's support are structural zeros and are skipped.
-  __syncwarp();                      // all reads of oMi (aliased by Hs) and bs writes are done
-  if (lane < NV) {
-    double2* dst = reinterpret_cast<double2*>(AsT + lane * WBC_LDT);
-#pragma unroll
-    for (int r = 0; r < 18; ++r) dst[r] = make_double2(a[2 * r], a[2 * r + 1]);
-    double* Hrow = Hs + lane * LD;
-#pragma unroll
-    for (int l = 0; l < NV; ++l) Hrow[l] = (l == lane) ? aj * aj : 0.0;
-  }
-  __syncwarp();
-  double gk = 0.0;
-  if (lane < NV) {
-#pragma unroll
-    for (int r = 0; r < 36; ++r) gk -= a[r] * bs[r];
-    gk -= aj * bj;
-  }
+  const long long stride = (long long)gridDim.x * wpc;
+  int buf = 0;
   {
-    double* Hrow = Hs + (lane < NV ? lane : 0) * LD;
+    long long s0 = (long long)blockIdx.x * wpc + warp;
+    if (s0 >= P.N) s0 = P.N - 1;
+    prefetch_inputs<NV>(P.io, s0, in0_a, lane);
+  }
+  for (long long base = (long long)blockIdx.x * wpc; base < P.N; base += stride) {
+    long long sidx = base + warp;
+    const bool valid = sidx < P.N;
+    if (!valid) sidx = P.N - 1;
+    if (DEBUG_OUT && !valid) break;
+    const uint32_t in_a = in0_a + 8 * WBC_IN_TOTAL * buf;
+    const uint32_t q_a = in_a + 8 * WBC_IN_Q, tg_a = in_a + 8 * WBC_IN_TARGETS;
+    const uint32_t mem_a = in_a + 8 * WBC_IN_MEM, ref_a = in_a + 8 * WBC_IN_REF;
+    cp_async_wait_all();
+    phase_sync<PS>();
+
+    // ---------------------------------------------------------------- kinematics
+    warp_fk_a(M_a, q_a, omi_a, lane);
+    double Sc[6];                        // column `lane` of data.J (WORLD): [lin; ang]
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Sc[i] = 0.0;
+    if (lane < NV) {
+      const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(col_joint) + 4 * lane);
+      double R[9], axl[3], aw[3];
+      lds_mat3(Ta, R);
+      lds_vec3(M_a + WBC_MOFF(col_axis) + 24 * lane, axl);
+      mat3_vec(R, axl, aw);
+      if (lds_s32(M_a + WBC_MOFF(col_ang) + 4 * lane)) {
+        double p[3];
+        lds_vec3(Ta + 72, p);
+        cross3(p, aw, Sc);
+        Sc[3] = aw[0]; Sc[4] = aw[1]; Sc[5] = aw[2];
+      } else {
+        Sc[0] = aw[0]; Sc[1] = aw[1]; Sc[2] = aw[2];
+      }
+    }
+    if (lane < WBC_HOT_FRAMES) {         // hot frames: 5 EE + trunk
+      const uint32_t Pa = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(frame_parent) + 4 * lane);
+      double Rp[9], R[9], p[3], fp[3], pp[3];
+      lds_mat3(Pa, Rp);
+      lds_vec3(Pa + 72, pp);
+      lds_vec3(M_a + WBC_MOFF(frp) + 24 * lane, fp);
+      if (lds_s32(M_a + WBC_MOFF(fr_ident) + 4 * lane)) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = Rp[i];
+      } else {
+        double FR[9];
+        lds_mat3(M_a + WBC_MOFF(frR) + 72 * lane, FR);
+        mat3_mul(Rp, FR, R);
+      }
+      mat3_vec(Rp, fp, p);
+      const uint32_t oa = omf_a + 8 * WBC_T_STRIDE * lane;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) sts_f64(oa + 8 * i, R[i]);
+      sts_f64(oa + 72, p[0] + pp[0]); sts_f64(oa + 80, p[1] + pp[1]); sts_f64(oa + 88, p[2] + pp[2]);
+    }
+    // centre of mass (only when the CoM constraint is on): lane j -> m_j * c_j in the world
+    double com_w[3] = {0, 0, 0};
+    double Jcom[2] = {0, 0};
+    if (cfg.constraint_mask & WBC_CON_COM) {
+      double mc[4] = {0, 0, 0, 0};
+      const int nj = lds_s32(M_a + WBC_MOFF(njoints));
+      if (lane >= 1 && lane < nj) {
+        const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lane;
+        double R[9], c[3], cl[3], pj[3];
+        lds_mat3(Ta, R);
+        lds_vec3(Ta + 72, pj);
+        lds_vec3(M_a + WBC_MOFF(com) + 24 * lane, cl);
+        mat3_vec(R, cl, c);
+        const double m = lds_f64(M_a + WBC_MOFF(mass) + 8 * lane);
+        mc[0] = m; mc[1] = m * (c[0] + pj[0]); mc[2] = m * (c[1] + pj[1]); mc[3] = m * (c[2] + pj[2]);
+      }
+      // subtree sums for my column: sum over joints j in sub_joints[lane]
+      double sm = 0, s1 = 0, s2 = 0, s3 = 0;
+      const uint32_t sub = (lane < NV) ? (uint32_t)lds_s32(M_a + WBC_MOFF(sub_joints) + 4 * lane) : 0u;
+      for (int j = 1; j < nj; ++j) {
+        const double m0 = __shfl_sync(WBC_FULL_MASK, mc[0], j), m1 = __shfl_sync(WBC_FULL_MASK, mc[1], j);
+        const double m2 = __shfl_sync(WBC_FULL_MASK, mc[2], j), m3 = __shfl_sync(WBC_FULL_MASK, mc[3], j);
+        if ((sub >> j) & 1u) { sm += m0; s1 += m1; s2 += m2; s3 += m3; }
+      }
+      const double Mt = lds_f64(M_a + WBC_MOFF(total_mass));
+      com_w[0] = warp_sum(mc[1]) / Mt; com_w[1] = warp_sum(mc[2]) / Mt; com_w[2] = warp_sum(mc[3]) / Mt;
+      // Jcom column = (sm * lin - (sum m c) x ang) / M   (only x, y rows are used, :670)
+      const double msc[3] = {s1, s2, s3};
+      double cx[3];
+      cross3(msc, Sc + 3, cx);
+      Jcom[0] = (sm * Sc[0] - cx[0]) / Mt;
+      Jcom[1] = (sm * Sc[1] - cx[1]) / Mt;
+    }
+    phase_sync<PS>();
+
+    // ---------------------------------------------------------------- task rows for my column (registers)
+    // EE tasks: A = W (J_LWA w) (:476-482); trunk task: A = (W J_WORLD) w (:488-490)
+    uint32_t supp[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) supp[t] = (uint32_t)lds_s32(M_a + WBC_MOFF(frame_supp) + 4 * t);
+    double a[36];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      const bool on = (cfg.task_mask >> t) & 1;
+      if (on) {
+        double Jc[6], fp[3];
+        lds_vec3(omf_a + 8 * (WBC_T_STRIDE * t + 9), fp);
+        frame_jac_lwa(Sc, (supp[t] >> lane) & 1u, fp, t == 5, Jc);
+        const double w = cfg.cart_task_weight[t];
+        if (w_ident) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) a[6 * t + r] = Jc[r] * w;
+        } else {
+          const double* W = (t < 5) ? cfg.ee_weight[t] : cfg.trunk_weight;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            double sacc = 0.0;
+            if (t < 5) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) sacc += W[6 * r + c] * (Jc[c] * w);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) sacc += W[6 * r + c] * Jc[c];
+              sacc *= w;
+            }
+            a[6 * t + r] = sacc;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) a[6 * t + r] = 0.0;
+      }
+    }
+
+    // ---------------------------------------------------------------- targets b (lanes 0..5), constraint bounds
+    // calcTargetVelEE3 (:1052-1157) on lanes 0..4 and calcTargetVelTrunk2 (:948-1015) on lane 5 share the
+    // position law and the Euler -> quaternion -> matrix chain; they differ in the skew product and the trunk's
+    // quaternion-error term.
+    sts_f64(clb_a + 8 * lane, 0.0);
+    sts_f64(cub_a + 8 * lane, 0.0);
+    __syncwarp();
+    if (lane < 6) {
+      const bool on = (cfg.task_mask >> lane) & 1;
+      const bool is_trunk = lane == 5;
+      const uint32_t T_a = omf_a + 8 * WBC_T_STRIDE * lane;
+      double b6[6] = {0, 0, 0, 0, 0, 0};
+      double fkq[4] = {0, 0, 0, 1};
+      if (is_trunk) {
+        double Rf[9];
+        lds_mat3(T_a, Rf);
+        scipy_quat_from_matrix(Rf, fkq);
+      }
+      if (on) {
+        const uint32_t prev_a = mem_a + 8 * (is_trunk ? MEM_PREV_TRUNK_REF : MEM_PREV_EE_POS + 3 * lane);
+        const uint32_t prevR_a = mem_a + 8 * (is_trunk ? MEM_OLD_TRUNK_ROT : MEM_PREV_EE_ROT + 9 * lane);
+        double target[3], prev[3], fk[3], ref_vel[3], err[3], ge[3], eul[3];
+        lds_vec3(tg_a + 24 * lane, target);
+        lds_vec3(prev_a, prev);
+        lds_vec3(T_a + 72, fk);
+        lds_vec3(ref_a + 8 * (REF_DEF_EE_ORI + 3 * lane), eul);        // default_trunk_ori follows the five EE entries
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          ref_vel[k] = (target[k] - prev[k]) * inv_dt;
+          err[k] = (target[k] - fk[k]) * inv_dt;
+        }
+        const double* G = is_trunk ? cfg.trunk_gain_pos : cfg.ee_gain_pos[lane < 5 ? lane : 0];
+        mat3_vec(G, err, ge);
+        double qref[4], Rref[9], prevR[9], dR[9], X[9], sk[9];
+        scipy_quat_from_euler_xyz(eul, qref);
+        scipy_matrix_from_quat(qref, Rref);
+        lds_mat3(prevR_a, prevR);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dR[k] = (Rref[k] - prevR[k]) * inv_dt;
+        // EE: (dR/dt) Rref^T (:1125); trunk: (dR/dt) Rref, NOT transposed (:984)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) X[3 * i + j] = is_trunk ? Rref[3 * i + j] : Rref[3 * j + i];
+        mat3_mul(dR, X, sk);
+        const double wgt = cfg.cart_task_weight[lane];
+        double o3 = sk[7], o4 = sk[2], o5 = sk[3];                      // skew[2,1], skew[0,2], skew[1,0]
+        if (is_trunk) {                                                 // quaternion error (:976), z term: the w*z products cancel
+          const double* f = fkq; const double* r = qref;
+          o3 += cfg.trunk_gain_ori[0] * ((f[3] * r[0]) - (f[0] * r[3]) + (f[1] * r[2]) - (f[2] * r[1]));
+          o4 += cfg.trunk_gain_ori[1] * ((f[3] * r[1]) - (f[1] * r[3]) - (f[0] * r[2]) + (f[2] * r[0]));
+          o5 += cfg.trunk_gain_ori[2] * ((f[0] * r[1]) - (f[1] * r[0]));
+        }
+        b6[0] = (ref_vel[0] + ge[0]) * wgt;
+        b6[1] = (ref_vel[1] + ge[1]) * wgt;
+        b6[2] = (ref_vel[2] + ge[2]) * wgt;
+        b6[3] = o3 * wgt; b6[4] = o4 * wgt; b6[5] = o5 * wgt;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sts_f64(prev_a + 8 * k, target[k]);   // :995 / :1151
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sts_f64(prevR_a + 8 * k, Rref[k]);    // :996 / :1152
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) sts_f64(bs_a + 8 * (6 * lane + r), b6[r]);
+      if (is_trunk && row_trunk >= 0) {                                  // trunkConstraint (:707-754)
+        double eul[3], ip[3], ie[3];
+        scipy_euler_xyz_from_quat(fkq, eul);
+        lds_vec3(ref_a + 8 * REF_INIT_TRUNK_POS, ip);
+        lds_vec3(ref_a + 8 * REF_INIT_TRUNK_EUL, ie);
+        const double cur[4] = {lds_f64(T_a + 88), eul[0], eul[1], eul[2]};
+        const double z_var = ip[2] * 0.25;
+        const double var = 1.5 * 0.1;
+        const double lo[4] = {ip[2] - z_var, ie[0] - var, ie[1] - var, ie[2] - var};
+        const double up[4] = {ip[2] + z_var, ie[0] + var, ie[1] + var, ie[2] + var};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          sts_f64(clb_a + 8 * (row_trunk + r), ((lo[r] - cur[r]) * inv_dt) * 0.5);
+          sts_f64(cub_a + 8 * (row_trunk + r), ((up[r] - cur[r]) * inv_dt) * 0.5);
+        }
+      }
+    }
+    if (row_com >= 0 && lane == 0) {                               // CoMConstraint (:669-694)
+      double FL[3], RR[3];
+      lds_vec3(omf_a + 8 * (1 * WBC_T_STRIDE + 9), FL);
+      lds_vec3(omf_a + 8 * (2 * WBC_T_STRIDE + 9), RR);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sts_f64(clb_a + 8 * (row_com + r), ((RR[r] - com_w[r]) * inv_dt) * 0.8);
+        sts_f64(cub_a + 8 * (row_com + r), ((FL[r] - com_w[r]) * inv_dt) * 0.8);
+      }
+    }
+    if (lane < cfg.n_extra_rows) {
+      sts_f64(clb_a + 8 * (row_extra + lane), cfg.extra_lo[lane]);
+      sts_f64(cub_a + 8 * (row_extra + lane), cfg.extra_hi[lane]);
+    }
+
+    // ---------------------------------------------------------------- box bounds, joint task
+    double lbv = 0.0, ubv = 0.0;
+    if (lane < NV) damper_bounds_a(M_a, cfg, q_a, lane, lbv, ubv);
+    double bj = 0.0;
+    if (joint_on && cfg.joint_mode == WBC_JOINT_PREV && lane < NV)               // qpJointb "PREV" (:1216-1217)
+      bj = ((1.0 / NV) * lds_f64(q_a + 8 * ((lane < 6) ? lane : lane + 1))) * cfg.joint_task_weight;
+
+    // ---------------------------------------------------------------- H = A^T A, g = -A^T b
+    // Column `lane` of the 36 Cartesian rows goes to shared memory transposed (AsT[lane][r]); then for every
+    // (task t, supporting column l) pair lane i adds  sum_r A[6t+r][i] A[6t+r][l]  to H[i][l]: three 128-bit
+    // broadcast loads and six FMAs.  Pairs outside the frame's support are structural zeros and are skipped.
+    __syncwarp();                      // all reads of oMi (aliased by Hs) and bs writes are done
+    const uint32_t hrow_a = hs_a + 8 * LD * (lane < NV ? lane : 0);
+    if (lane < NV) {
+      const uint32_t da = ast_a + 8 * WBC_LDT * lane;
+#pragma unroll
+      for (int r = 0; r < 18; ++r) sts_f64x2(da + 16 * r, a[2 * r], a[2 * r + 1]);
+#pragma unroll
+      for (int l = 0; l < NV; ++l) sts_f64(hrow_a + 8 * l, 0.0);
+    }
+    __syncwarp();
+    double gk = 0.0;
+    {
+      double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 18; ++r) {
+        const double2 b2 = lds_f64x2(bs_a + 16 * r);
+        g0 = fma(-a[2 * r], b2.x, g0);
+        g1 = fma(-a[2 * r + 1], b2.y, g1);
+      }
+      gk = (g0 + g1) - aj * bj;
+    }
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
       if (!((cfg.task_mask >> t) & 1)) continue;
-      uint32_t mask = M->frame_supp[t];
+      uint32_t mask = supp[t];
       while (mask) {                                               // warp-uniform
         const int l = __ffs(mask) - 1;
         mask &= mask - 1;
-        const double2* c2 = reinterpret_cast<const double2*>(AsT + l * WBC_LDT + 6 * t);
-        const double2 v0 = c2[0], v1 = c2[1], v2 = c2[2];
-        double h0 = a[6 * t] * v0.x, h1 = a[6 * t + 1] * v0.y;
+        const uint32_t ca = ast_a + 8 * (WBC_LDT * l + 6 * t);
+        const double2 v0 = lds_f64x2(ca), v1 = lds_f64x2(ca + 16), v2 = lds_f64x2(ca + 32);
+        const uint32_t ha = hrow_a + 8 * l;
+        const double hprev = lds_f64(ha);
+        double h0 = fma(a[6 * t], v0.x, hprev), h1 = a[6 * t + 1] * v0.y;
         h0 = fma(a[6 * t + 2], v1.x, h0); h1 = fma(a[6 * t + 3], v1.y, h1);
         h0 = fma(a[6 * t + 4], v2.x, h0); h1 = fma(a[6 * t + 5], v2.y, h1);
-        if (lane < NV) Hrow[l] += h0 + h1;
+        if (lane < NV) sts_f64(ha, h0 + h1);
       }
     }
-  }
-  __syncwarp();
+    __syncwarp();
 
-  if (DEBUG_OUT) {
-    const WbcAssembleOut& D = P.dbg;
-    const int m = P.m_rows;
+    if (DEBUG_OUT) {
+      const WbcAssembleOut& D = P.dbg;
+      const int m = P.m_rows;
+      if (lane < NV) {
+        int row = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          if (!((cfg.task_mask >> t) & 1)) continue;
+#pragma unroll
+          for (int r = 0; r < 6; ++r, ++row) {
+            if (D.A) D.A[(sidx * m + row) * NV + lane] = a[6 * t + r];
+            if (D.b && lane == 0) D.b[sidx * m + row] = lds_f64(bs_a + 8 * (6 * t + r));
+          }
+        }
+        if (joint_on) {
+          for (int r = 0; r < NV; ++r) {
+            if (D.A) D.A[(sidx * m + row + r) * NV + lane] = (r == lane) ? aj : 0.0;
+          }
+          if (D.b) D.b[sidx * m + row + lane] = bj;
+        }
+        if (D.lb) D.lb[sidx * NV + lane] = lbv;
+        if (D.ub) D.ub[sidx * NV + lane] = ubv;
+        if (D.g) D.g[sidx * NV + lane] = gk;
+        if (D.H)
+          for (int l = 0; l < NV; ++l)
+            D.H[(sidx * NV + lane) * NV + l] = lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0);
+      }
+      __syncwarp();
+    }
+
+    // ---------------------------------------------------------------- constraint rows (AsT is dead now)
     if (lane < NV) {
-      int row = 0;
-      for (int t = 0; t < 6; ++t) {
-        if (!((cfg.task_mask >> t) & 1)) continue;
-        for (int r = 0; r < 6; ++r, ++row) {
-          if (D.A) D.A[(sidx * m + row) * NV + lane] = AsT[lane * WBC_LDT + 6 * t + r];
-          if (D.b && lane == 0) D.b[sidx * m + row] = bs[6 * t + r];
+      const uint32_t c_a = ast_a + 8 * lane;
+      if (row_com >= 0) { sts_f64(c_a + 8 * LD * row_com, Jcom[0]); sts_f64(c_a + 8 * LD * (row_com + 1), Jcom[1]); }
+      if (row_trunk >= 0) {                                        // LWA rows z, wx, wy, wz of the trunk frame (:709)
+        double Jc[6], fp[3];
+        lds_vec3(omf_a + 8 * (WBC_T_STRIDE * WBC_FRAME_TRUNK + 9), fp);
+        frame_jac_lwa(Sc, (supp[WBC_FRAME_TRUNK] >> lane) & 1u, fp, false, Jc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sts_f64(c_a + 8 * LD * (row_trunk + r), Jc[2 + r]);
+      }
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        if (row_ee[i] >= 0) {                                      // WORLD linear rows (:758)
+          const bool sup = (supp[i] >> lane) & 1u;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) sts_f64(c_a + 8 * LD * (row_ee[i] + r), sup ? Sc[r] : 0.0);
         }
       }
-      if (joint_on) {
-        for (int r = 0; r < NV; ++r) {
-          if (D.A) D.A[(sidx * m + row + r) * NV + lane] = (r == lane) ? aj : 0.0;
+      for (int e = 0; e < cfg.n_extra_rows; ++e) {                 // extension rows (not in the reference)
+        const int f = cfg.extra_frame[e];
+        double T[12], Jc[6];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T[i] = lds_f64(omf_a + 8 * (WBC_T_STRIDE * f + i));
+        frame_jac_column(Sc, (uint32_t)lds_s32(M_a + WBC_MOFF(frame_supp) + 4 * f), lane, T, cfg.extra_rf[e], Jc);
+        double sacc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sacc += cfg.extra_coeff[e][c] * Jc[c];
+        sts_f64(c_a + 8 * LD * (row_extra + e), sacc);
+      }
+    }
+    phase_sync<PS>();
+    const double clb_r = (lane < nC) ? lds_f64(clb_a + 8 * lane) : 0.0;
+    const double cub_r = (lane < nC) ? lds_f64(cub_a + 8 * lane) : 0.0;
+
+    if (DEBUG_OUT) {
+      const WbcAssembleOut& D = P.dbg;
+      if (D.C && lane < NV)
+        for (int r = 0; r < nC; ++r) D.C[(sidx * nC + r) * NV + lane] = lds_f64(ast_a + 8 * (LD * r + lane));
+      if (D.Clb && lane < nC) D.Clb[sidx * nC + lane] = clb_r;
+      if (D.Cub && lane < nC) D.Cub[sidx * nC + lane] = cub_r;
+      if (P.io.mem_out)
+        for (int i = lane; i < WBC_MEM_STRIDE; i += 32) P.io.mem_out[sidx * WBC_MEM_STRIDE + i] = lds_f64(mem_a + 8 * i);
+      __syncwarp();
+      if (base + stride < P.N) {
+        long long ns = base + stride + warp;
+        if (ns >= P.N) ns = P.N - 1;
+        prefetch_inputs<NV>(P.io, ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
+      }
+      buf ^= 1;
+      continue;
+    }
+
+    // ---------------------------------------------------------------- next state's inputs, then the QP
+    if (base + stride < P.N) {
+      long long ns = base + stride + warp;
+      if (ns >= P.N) ns = P.N - 1;
+      prefetch_inputs<NV>(P.io, ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
+    }
+    double x;
+    QpResult res;
+    {
+      double h[NV];
+#pragma unroll
+      for (int l = 0; l < NV; ++l) h[l] = (lane < NV) ? lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0) : 0.0;
+      const double hdiag = (lane < NV) ? lds_f64(hrow_a + 8 * lane) + aj * aj : 0.0;
+      __syncwarp();                    // Hs becomes the solver's R factor
+      QpRegShared S;
+      S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
+      res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
+    }
+
+    phase_sync<PS>();
+    if (valid && lane < NV) P.io.qdot[sidx * NV + lane] = x;
+    if (valid && lane == 0) {
+      P.io.status[sidx] = res.status;
+      P.io.iters[sidx] = res.iters;
+      if (P.io.active_set) {
+        P.io.active_set[2 * sidx] = res.act_box;
+        P.io.active_set[2 * sidx + 1] = res.act_rows;
+      }
+    }
+    if (valid && P.io.mem_out)
+      for (int i = lane; i < WBC_MEM_STRIDE; i += 32) P.io.mem_out[sidx * WBC_MEM_STRIDE + i] = lds_f64(mem_a + 8 * i);
+
+    // ---------------------------------------------------------------- integrate + base estimate
+    if (P.io.q_next) {
+      __syncwarp();
+      const double v = x * dt;
+      double vb[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) vb[i] = __shfl_sync(WBC_FULL_MASK, v, i);
+      const uint32_t qn_a = ws_a + 8 * L.col;          // [<= 33] new configuration (the 64-double column buffer is free now)
+      if (lane == 0) {
+        double q7[7], o7[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) q7[i] = lds_f64(q_a + 8 * i);
+        integrate_freeflyer(q7, vb, o7);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) sts_f64(qn_a + 8 * i, o7[i]);
+      }
+      if (lane >= 6 && lane < NV) {
+        const int iq = lds_s32(M_a + WBC_MOFF(col_q) + 4 * lane);
+        sts_f64(qn_a + 8 * iq, lds_f64(q_a + 8 * iq) + v);
+      }
+      __syncwarp();
+      if (!(P.flags & WBC_STEP_FLAG_PLAIN_INTEGRATE)) {
+        // updateState(joint_config, imu, running=True): q = [old xyz, imu quat, joints], FK, trunkWorldPos (:387-428)
+        if (lane < 3) sts_f64(qn_a + 8 * lane, lds_f64(q_a + 8 * lane));
+        if (P.io.imu_quat && lane < 4) sts_f64(qn_a + 8 * (3 + lane), P.io.imu_quat[sidx * 4 + lane]);
+        __syncwarp();
+        warp_fk_a(M_a, qn_a, omi_a, lane);
+        double bp[3] = {0, 0, 0};
+        if (lane < 4) {                // foot frame positions at the new configuration
+          const uint32_t Pa = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(frame_parent) + 4 * lane);
+          double Rp[9], fp[3];
+          lds_mat3(Pa, Rp);
+          lds_vec3(M_a + WBC_MOFF(frp) + 24 * lane, fp);
+          mat3_vec(Rp, fp, bp);
+          bp[0] += lds_f64(Pa + 72); bp[1] += lds_f64(Pa + 80); bp[2] += lds_f64(Pa + 88);
         }
-        if (D.b) D.b[sidx * m + row + lane] = bj;
+        // trunkWorldPos (:1297-1327): order of the sums follows the reference (FR + FL + RR + RL) / 4
+        double BPA[3], WPA[3], Rt[9], pt[3];
+        {
+          const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(frame_parent) + 4 * WBC_FRAME_TRUNK);
+          double Rp[9], FR[9], fp[3];
+          lds_mat3(Ta, Rp);
+          lds_mat3(M_a + WBC_MOFF(frR) + 72 * WBC_FRAME_TRUNK, FR);
+          lds_vec3(M_a + WBC_MOFF(frp) + 24 * WBC_FRAME_TRUNK, fp);
+          mat3_mul(Rp, FR, Rt);
+          mat3_vec(Rp, fp, pt);
+          pt[0] += lds_f64(Ta + 72); pt[1] += lds_f64(Ta + 80); pt[2] += lds_f64(Ta + 88);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double d0 = __shfl_sync(WBC_FULL_MASK, bp[c], 0) - pt[c];
+          const double d1 = __shfl_sync(WBC_FULL_MASK, bp[c], 1) - pt[c];
+          const double d2 = __shfl_sync(WBC_FULL_MASK, bp[c], 2) - pt[c];
+          const double d3 = __shfl_sync(WBC_FULL_MASK, bp[c], 3) - pt[c];
+          BPA[c] = (d0 + d1 + d2 + d3) / 4;
+          WPA[c] = (lds_f64(tg_a + 8 * c) + lds_f64(tg_a + 8 * (3 + c)) + lds_f64(tg_a + 8 * (6 + c)) + lds_f64(tg_a + 8 * (9 + c))) / 4;
+        }
+        double rb[3];
+        mat3_vec(Rt, BPA, rb);
+        __syncwarp();
+        if (lane < 3) sts_f64(qn_a + 8 * lane, WPA[lane] - rb[lane]);
+        __syncwarp();
       }
-      if (D.lb) D.lb[sidx * NV + lane] = lbv;
-      if (D.ub) D.ub[sidx * NV + lane] = ubv;
-      if (D.g) D.g[sidx * NV + lane] = gk;
-      if (D.H)
-        for (int l = 0; l < NV; ++l) D.H[(sidx * NV + lane) * NV + l] = Hs[lane * LD + l];
-    }
-    __syncwarp();
-  }
-
-  // ---------------------------------------------------------------- constraint rows (AsT is dead now)
-  if (lane < NV) {
-    if (row_com >= 0) { Cs[(row_com + 0) * LD + lane] = Jcom[0]; Cs[(row_com + 1) * LD + lane] = Jcom[1]; }
-    if (row_trunk >= 0) {                                        // LWA rows z, wx, wy, wz of the trunk frame (:709)
-      double Jc[6];
-      frame_jac_column(Sc, M->frame_supp[WBC_FRAME_TRUNK], lane, oMf + WBC_FRAME_TRUNK * WBC_T_STRIDE,
-                       WBC_RF_LOCAL_WORLD_ALIGNED, Jc);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) Cs[(row_trunk + r) * LD + lane] = Jc[2 + r];
-    }
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      if (row_ee[i] >= 0) {                                      // WORLD linear rows (:758)
-        const bool sup = (M->frame_supp[i] >> lane) & 1u;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) Cs[(row_ee[i] + r) * LD + lane] = sup ? Sc[r] : 0.0;
-      }
-    }
-    for (int e = 0; e < cfg.n_extra_rows; ++e) {                 // extension rows (not in the reference)
-      const int f = cfg.extra_frame[e];
-      double Jc[6];
-      frame_jac_column(Sc, M->frame_supp[f], lane, oMf + f * WBC_T_STRIDE, cfg.extra_rf[e], Jc);
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s += cfg.extra_coeff[e][c] * Jc[c];
-      Cs[(row_extra + e) * LD + lane] = s;
-    }
-  }
-  phase_sync<PS>();
-  const double clb_r = (lane < nC) ? clbs[lane] : 0.0;
-  const double cub_r = (lane < nC) ? cubs[lane] : 0.0;
-
-  if (DEBUG_OUT) {
-    const WbcAssembleOut& D = P.dbg;
-    if (D.C && lane < NV)
-      for (int r = 0; r < nC; ++r) D.C[(sidx * nC + r) * NV + lane] = Cs[r * LD + lane];
-    if (D.Clb && lane < nC) D.Clb[sidx * nC + lane] = clb_r;
-    if (D.Cub && lane < nC) D.Cub[sidx * nC + lane] = cub_r;
-    if (P.io.mem_out)
-      for (int i = lane; i < WBC_MEM_STRIDE; i += 32) P.io.mem_out[sidx * WBC_MEM_STRIDE + i] = io[WBC_IO_MEM + i];
-    return;
-  }
-
-  // ---------------------------------------------------------------- QP
-  double x;
-  QpResult res;
-  {
-    double h[NV];
-    const double* Hrow = Hs + (lane < NV ? lane : 0) * LD;
-#pragma unroll
-    for (int l = 0; l < NV; ++l) h[l] = (lane < NV) ? Hrow[l] : 0.0;
-    const double hdiag = (lane < NV) ? Hrow[lane] : 0.0;
-    __syncwarp();                    // Hs becomes the solver's R factor
-    QpRegShared S;
-    S.R = Hs; S.col = ws + L.col; S.vd = vd; S.C = Cs;
-    res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
-  }
-
-  phase_sync<PS>();
-  if (valid && lane < NV) P.io.qdot[sidx * NV + lane] = x;
-  if (valid && lane == 0) {
-    P.io.status[sidx] = res.status;
-    P.io.iters[sidx] = res.iters;
-    if (P.io.active_set) {
-      P.io.active_set[2 * sidx] = res.act_box;
-      P.io.active_set[2 * sidx + 1] = res.act_rows;
-    }
-  }
-  if (valid && P.io.mem_out)
-    for (int i = lane; i < WBC_MEM_STRIDE; i += 32) P.io.mem_out[sidx * WBC_MEM_STRIDE + i] = io[WBC_IO_MEM + i];
-
-  // ---------------------------------------------------------------- integrate + base estimate
-  if (P.io.q_next) {
-    __syncwarp();
-    const double v = x * dt;
-    double vb[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) vb[i] = __shfl_sync(WBC_FULL_MASK, v, i);
-    double* qn = ws + L.col;         // [<= 33] new configuration (the 64-double column buffer is free now)
-    if (lane == 0) {
-      double o7[7];
-      integrate_freeflyer(qs, vb, o7);
-#pragma unroll
-      for (int i = 0; i < 7; ++i) qn[i] = o7[i];
-    }
-    if (lane >= 6 && lane < NV) {
-      const int iq = M->col_q[lane];
-      qn[iq] = qs[iq] + v;
-    }
-    __syncwarp();
-    if (!(P.flags & WBC_STEP_FLAG_PLAIN_INTEGRATE)) {
-      // updateState(joint_config, imu, running=True): q = [old xyz, imu quat, joints], FK, trunkWorldPos (:387-428)
-      if (lane < 3) qn[lane] = qs[lane];
-      if (P.io.imu_quat && lane < 4) qn[3 + lane] = P.io.imu_quat[sidx * 4 + lane];
-      __syncwarp();
-      warp_fk(M, qn, oMi, lane);
-      double bp[3] = {0, 0, 0};
-      if (lane < 4) {                // foot frame positions at the new configuration
-        const int par = M->frame_parent[lane];
-        const double* Pm = oMi + par * WBC_T_STRIDE;
-        double Rp[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Rp[i] = Pm[i];
-        mat3_vec(Rp, M->frp[lane], bp);
-        bp[0] += Pm[9]; bp[1] += Pm[10]; bp[2] += Pm[11];
-      }
-      // trunkWorldPos (:1297-1327): order of the sums follows the reference (FR + FL + RR + RL) / 4
-      double BPA[3], WPA[3];
-      const double* Tt = oMi + M->frame_parent[WBC_FRAME_TRUNK] * WBC_T_STRIDE;   // trunk frame has identity offset?
-      double Rt[9], pt[3];
-      {
-        double Rp[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Rp[i] = Tt[i];
-        mat3_mul(Rp, M->frR[WBC_FRAME_TRUNK], Rt);
-        mat3_vec(Rp, M->frp[WBC_FRAME_TRUNK], pt);
-        pt[0] += Tt[9]; pt[1] += Tt[10]; pt[2] += Tt[11];
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double d0 = __shfl_sync(WBC_FULL_MASK, bp[c], 0) - pt[c];
-        const double d1 = __shfl_sync(WBC_FULL_MASK, bp[c], 1) - pt[c];
-        const double d2 = __shfl_sync(WBC_FULL_MASK, bp[c], 2) - pt[c];
-        const double d3 = __shfl_sync(WBC_FULL_MASK, bp[c], 3) - pt[c];
-        BPA[c] = (d0 + d1 + d2 + d3) / 4;
-        const double* tg = io + WBC_IO_TARGETS;
-        WPA[c] = (tg[c] + tg[3 + c] + tg[6 + c] + tg[9 + c]) / 4;
-      }
-      double rb[3];
-      mat3_vec(Rt, BPA, rb);
-      if (lane < 3) qn[lane] = WPA[lane] - rb[lane];
+      if (valid)
+        for (int i = lane; i < nq; i += 32) P.io.q_next[sidx * nq + i] = lds_f64(qn_a + 8 * i);
       __syncwarp();
     }
-    if (valid)
-      for (int i = lane; i < nq; i += 32) P.io.q_next[sidx * nq + i] = qn[i];
+    buf ^= 1;
   }
+  cp_async_wait_all();
 }
