@@ -273,11 +273,12 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
   constexpr int n = NV, LD = NV | 1;
   const int nC = P.nC;
   const int hs_sz = n * (n + 2) + (n & 1), cs_sz = (nC * LD + 1) & ~1;
-  double* ws = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (hs_sz + cs_sz + 96);
+  double* ws = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (hs_sz + cs_sz + 224);
   double* Hs = ws;
   double* Cs = ws + hs_sz;
   double* col = Cs + cs_sz;
   double* vd = col + 64;
+  double* bnd = vd + 32;         // clb[32] cub[32] dd[64]
   for (long long s = (long long)blockIdx.x * wpc + warp; s < P.N; s += (long long)gridDim.x * wpc) {
     double gk = 0.0;
     if (P.H) {
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
     if (nC > 0)
       for (int i = lane; i < nC * n; i += 32) Cs[(i / n) * LD + (i % n)] = P.C[s * (long long)nC * n + i];
     const double lbv = (lane < n) ? P.lb[s * n + lane] : 0.0, ubv = (lane < n) ? P.ub[s * n + lane] : 0.0;
-    const double clb = (lane < nC) ? P.Clb[s * nC + lane] : 0.0, cub = (lane < nC) ? P.Cub[s * nC + lane] : 0.0;
+    bnd[lane] = (lane < nC) ? P.Clb[s * nC + lane] : 0.0;
+    bnd[32 + lane] = (lane < nC) ? P.Cub[s * nC + lane] : 0.0;
     __syncwarp();
     double h[NV];
     const double* Hrow = Hs + (lane < n ? lane : 0) * LD;
@@ -313,8 +315,9 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
     __syncwarp();
     QpRegShared S;
     S.R = smem_addr(Hs); S.col = smem_addr(col); S.vd = smem_addr(vd); S.C = smem_addr(Cs);
+    S.clb = smem_addr(bnd); S.cub = S.clb + 8 * 32; S.dd = S.clb + 8 * 64;
     double x;
-    const QpResult res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, clb, cub, P.max_iter, x);
+    const QpResult res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, P.max_iter, x);
     if (lane < n) P.x[s * n + lane] = x;
     if (lane == 0) {
       P.status[s] = res.status;
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
 template <int NV, bool SPLIT>
 static int launch_qp_reg_k(const QpParams& P, int sms, cudaStream_t st) {
   const int LD = NV | 1, wpc = 8;
-  const int per_warp = NV * (NV + 2) + (NV & 1) + ((P.nC * LD + 1) & ~1) + 96;
+  const int per_warp = NV * (NV + 2) + (NV & 1) + ((P.nC * LD + 1) & ~1) + 224;
   const size_t smem = (size_t)wpc * per_warp * sizeof(double);
   auto kern = wbc_qp_reg_kernel<NV, SPLIT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -41,6 +41,8 @@ struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byt
   uint32_t col;      // [64]: 1 / L_kk
   uint32_t vd;       // [32]: broadcast vector
   uint32_t C;        // [nC][LD] constraint rows (read once; up to two doubles past the end are touched)
+  uint32_t clb, cub; // [32] each: row bounds (input)
+  uint32_t dd;       // [64]: |d|^2 of the box constraints [0, 32) and of the rows [32, 64)
 };
 
 // 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free
@@ -78,9 +80,8 @@ __device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
 
 template <int NV, bool SPLIT>
 __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
-                                                      const int nC, double g, const double lb, const double ub,
-                                                      const double clb, const double cub, const int max_iter,
-                                                      double& x_out) {
+                                                      const int nC, double g, const double lb_in, const double ub_in,
+                                                      const int max_iter, double& x_out) {
   constexpr int n = NV;
   constexpr int LD = NV | 1;
   constexpr int LC = (NV + 1) & ~1;          // column stride of the stored L (even: 128-bit broadcast loads)
@@ -108,20 +109,22 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   const double piv_min = WBC_QP_PIVOT_REL * fmax(hd, 0.0);
 
   // ---- fixed variables (lb == ub) are eliminated: row/column of H -> identity, g shifted -------------
-  const unsigned eqb = __ballot_sync(WBC_FULL_MASK, act && lb == ub);
+  // Per-lane bounds live in shared memory during the iterations (lo[0..32) | up[32..64) in `col` once the
+  // factorisation is done; row bounds in S.clb / S.cub): registers are the scarce resource of this kernel.
+  const unsigned eqb = __ballot_sync(WBC_FULL_MASK, act && lb_in == ub_in);
   const bool fixed = (eqb >> lane) & 1u;
   if (eqb) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       if ((eqb >> k) & 1u) {                            // warp-uniform
-        const double xk = __shfl_sync(WBC_FULL_MASK, lb, k);
+        const double xk = __shfl_sync(WBC_FULL_MASK, lb_in, k);
         g = fma(h[k], xk, g);
         h[k] = (lane == k) ? 1.0 : 0.0;
       } else if (fixed) {
         h[k] = 0.0;
       }
     }
-    if (fixed) g = -lb;
+    if (fixed) g = -lb_in;
     res.iters = __popc(eqb);
   }
   __syncwarp();
@@ -171,7 +174,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         if ((eqb >> k) & 1u) {
-          const double xk = __shfl_sync(WBC_FULL_MASK, lb, k);
+          const double xk = __shfl_sync(WBC_FULL_MASK, lb_in, k);
           const bool holder = !SPLIT || (upper == (k >= HALF));
           const int kl = (SPLIT && k >= HALF) ? k - HALF : k;
           if (holder) {
@@ -222,7 +225,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   }
 
   // ---- |d|^2 of every constraint (invariant under the orthogonal updates), x0 = -J (L^-1 g), C x0 -----
-  double ddJ, ddD, x, ax;
+  const uint32_t lo_a = rk_a, up_a = rk_a + 8 * 32;     // 1 / L_kk is dead now
+  double x, ax;
   {
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
@@ -235,10 +239,13 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       if (j & 1) b1 = fma(Dr[j], Dr[j], b1);
       else b0 = fma(Dr[j], Dr[j], b0);
     }
-    ddJ = a0 + a1;
-    ddD = b0 + b1;
+    double ddD = b0 + b1;
     if (SPLIT) ddD += __shfl_xor_sync(WBC_FULL_MASK, ddD, 16);
     __syncwarp();
+    sts_f64(S.dd + 8 * lane, a0 + a1);
+    if (!SPLIT || lane < 16) sts_f64(S.dd + 8 * (32 + lane), ddD);
+    sts_f64(lo_a + 8 * lane, lb_in);
+    sts_f64(up_a + 8 * lane, ub_in);
     if (lane == NV) publish_row<NV>(vd_a, Jr);
     __syncwarp();
     double x0 = 0.0, x1 = 0.0, c0 = 0.0, c1 = 0.0;
@@ -254,7 +261,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       c0 = fma(-Dr[2 * p], w2.x, c0);
       if (2 * p + 1 < ND) c1 = fma(-Dr[WBC_DX(2 * p + 1)], w2.y, c1);
     }
-    x = fixed ? lb : (x0 + x1);
+    x = fixed ? lb_in : (x0 + x1);
     double cx = c0 + c1;
     if (SPLIT) cx += __shfl_xor_sync(WBC_FULL_MASK, cx, 16);
     ax = cx + shift;
@@ -266,7 +273,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   int ws_c = -1, slot = lane;                // per working-set position (lane = position)
   double u = 0.0, rinv = 0.0;
   int bstat = fixed ? 3 : 0, cstat = 0;      // 0 none 1 lower 2 upper 3 eq
-  unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && clb == cub);
+  unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && lds_f64(S.clb + 8 * lane) == lds_f64(S.cub + 8 * lane));
 
   // One flat loop: every pass is one step of the method for the current candidate (pick one if there is none).
   bool have = false, is_eq = false, is_box = false;
@@ -286,13 +293,13 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
         int bidx = 0x7fffffff;
         int myside_b = -1, myside_c = -1;
         if (act && bstat == 0) {
-          const double slo = x - lb, sup = ub - x;
+          const double slo = x - lds_f64(lo_a + 8 * lane), sup = lds_f64(up_a + 8 * lane) - x;
           best = fmin(slo, sup);
           bidx = lane;
           myside_b = (slo <= sup) ? -1 : +1;
         }
         if (lane < nC && cstat == 0) {
-          const double slo = ax - clb, sup = cub - ax;
+          const double slo = ax - lds_f64(S.clb + 8 * lane), sup = lds_f64(S.cub + 8 * lane) - ax;
           const double v = fmin(slo, sup);
           myside_c = (slo <= sup) ? -1 : +1;
           if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
@@ -307,7 +314,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       sgn = (side > 0) ? -1.0 : 1.0;                               // normal = sgn * a_ip
       is_box = ip < n;
       owner = is_box ? ip : ip - n;
-      dd = __shfl_sync(WBC_FULL_MASK, is_box ? ddJ : ddD, owner);
+      dd = lds_f64(S.dd + 8 * (is_box ? owner : 32 + owner));
       u_new = 0.0;
       have = true;
     }
@@ -362,8 +369,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     double s_ip;
     {
       const double v_i = __shfl_sync(WBC_FULL_MASK, is_box ? x : ax, owner);
-      const double lo_i = __shfl_sync(WBC_FULL_MASK, is_box ? lb : clb, owner);
-      const double up_i = __shfl_sync(WBC_FULL_MASK, is_box ? ub : cub, owner);
+      const double lo_i = lds_f64((is_box ? lo_a : S.clb) + 8 * owner);
+      const double up_i = lds_f64((is_box ? up_a : S.cub) + 8 * owner);
       s_ip = (side > 0) ? (up_i - v_i) : (v_i - lo_i);
     }
     const bool dependent = dd2 <= WBC_QP_DEP_TOL * dd;
@@ -452,7 +459,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     }
     if (add) {
       // -------------------------------------------------------- full step: constraint ip enters at position iq
-      const double d_iq = __shfl_sync(WBC_FULL_MASK, d_own, iq);      // unsigned
+      const double d_iq = lds_f64(vd_a + 8 * iq);                     // unsigned (only entries below iq were zeroed)
       const double nrm = dd2 * rs;
       const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
       const double isig = (d_iq >= 0.0) ? rs : -rs;                   // 1 / sigma
@@ -511,7 +518,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     __syncwarp();
   }
 
-  x_out = fixed ? lb : x;
+  x_out = fixed ? lds_f64(lo_a + 8 * lane) : x;
   pack_active_sets(lane, n, nC, bstat, cstat, res);
   return res;
 }

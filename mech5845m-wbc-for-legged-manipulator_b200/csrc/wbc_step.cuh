@@ -53,7 +53,7 @@ __host__ __device__ inline StepLayout step_layout(int nv, int nC) {
   L.col = r0 + r1;
   L.omf = L.col + 64;
   L.vec = L.omf + WBC_HOT_FRAMES * WBC_T_STRIDE + 2;   // 6 * 13 + 2 = 80
-  L.in = L.vec + 32 + 32 + 32 + 40;                    // vd[32] clb[32] cub[32] bs[40]
+  L.in = L.vec + 32 + 32 + 32 + 64;                    // vd[32] clb[32] cub[32] bs[64] (b, then the QP's |d|^2)
   L.total = L.in + 2 * WBC_IN_TOTAL;
   L.total = (L.total + 1) & ~1;
   return L;
@@ -668,8 +668,8 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       }
     }
     phase_sync<PS>();
-    const double clb_r = (lane < nC) ? lds_f64(clb_a + 8 * lane) : 0.0;
-    const double cub_r = (lane < nC) ? lds_f64(cub_a + 8 * lane) : 0.0;
+    const double clb_r = (DEBUG_OUT && lane < nC) ? lds_f64(clb_a + 8 * lane) : 0.0;
+    const double cub_r = (DEBUG_OUT && lane < nC) ? lds_f64(cub_a + 8 * lane) : 0.0;
 
     if (DEBUG_OUT) {
       const WbcAssembleOut& D = P.dbg;
@@ -705,7 +705,8 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       __syncwarp();                    // Hs becomes the solver's R factor
       QpRegShared S;
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
-      res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, clb_r, cub_r, cfg.max_iter, x);
+      S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
+      res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
     }
 
     phase_sync<PS>();
