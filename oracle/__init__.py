@@ -5,6 +5,11 @@ path (``wrappers/Robot_Wrapper4.py`` + ``wrappers/QP_Wrapper.py``) and of the th
 semantics it sits on (Pinocchio rigid-body kinematics, qpOASES QP solve).  It exists to
 CHECK the CUDA path; it is never the thing that is shipped or measured.
 
+Two restatements live here: the NumPy/SciPy one (``pin.py``, ``rotation_port.py``, ``qp_wrapper.py``,
+``robot_wrapper4.py``), which mirrors the reference class by class, and a plain-C one (``wbc_oracle.c``, loaded by
+``c_port.py``) that is pinned against the first (``tests/test_oracle_c_cpu.py``) and is fast enough to check
+every state of a 4096-state batch and to serve as the timed CPU baseline.
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import it.  The product package
 (``mech5845m-wbc-for-legged-manipulator_b200``) must never import anything from here.

@@ -201,3 +201,24 @@ def test_full_size_properties_config2():
         Nm = np.array(normals).T
         lam, *_ = np.linalg.lstsq(Nm, gn[s], rcond=None)
         assert np.abs(Nm @ lam - gn[s]).max() < 1e-7, s
+
+
+def test_config2_every_state_against_the_c_oracle():
+    """BASELINE config 2: A1 + PX100, 4096 random states, every solution compared with the CPU loop
+    (oracle/wbc_oracle.c, itself pinned against the NumPy/SciPy oracle on the CPU)."""
+    from oracle import c_port
+    N = 4096
+    for sigma in (5e-4, 5e-3):
+        robot = _robot("a1_px100_pin_ver", N, P1_TASKS, P2_CONS, True)
+        q, targets = _load(robot, N, 20260001, sigma)
+        mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+        x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=True).cpu().numpy()
+        ts, table = c_port.table_struct("a1_px100_pin_ver")
+        ref = c_port.step(ts, c_port.config_struct(robot, table), q, targets.cpu().numpy(), mem0.cpu().numpy(),
+                          ref0.cpu().numpy(), robot.dt)
+        assert (robot.last_status.cpu().numpy() == 0).all() and (ref["status"] == 0).all()
+        assert np.abs(x - ref["qdot"]).max() < QP_TOL
+        assert (robot.last_iters.cpu().numpy() == ref["iters"]).all()
+        act = robot.last_active_set.cpu().numpy().astype(np.uint64)
+        assert (act == ref["active_set"]).all()
+        assert np.abs(robot._mem.cpu().numpy() - ref["mem_out"]).max() < 1e-12
