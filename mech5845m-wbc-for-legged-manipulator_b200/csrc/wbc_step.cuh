@@ -587,10 +587,24 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       }
       gk = (g0 + g1) - aj * bj;
     }
+    // The six free-flyer columns support every frame: 36 of the 53 (task, column) pairs.  They accumulate in
+    // registers as independent chains; only the limb columns go through the shared-memory read-modify-write.
+    double hb[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
       if (!((cfg.task_mask >> t) & 1)) continue;
-      uint32_t mask = supp[t];
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        if ((supp[t] >> l) & 1u) {                                 // warp-uniform
+          const uint32_t ca = ast_a + 8 * (WBC_LDT * l + 6 * t);
+          const double2 v0 = lds_f64x2(ca), v1 = lds_f64x2(ca + 16), v2 = lds_f64x2(ca + 32);
+          double h0 = fma(a[6 * t], v0.x, hb[l]), h1 = a[6 * t + 1] * v0.y;
+          h0 = fma(a[6 * t + 2], v1.x, h0); h1 = fma(a[6 * t + 3], v1.y, h1);
+          h0 = fma(a[6 * t + 4], v2.x, h0); h1 = fma(a[6 * t + 5], v2.y, h1);
+          hb[l] = h0 + h1;
+        }
+      }
+      uint32_t mask = supp[t] & ~0x3Fu;
       while (mask) {                                               // warp-uniform
         const int l = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -603,6 +617,10 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
         h0 = fma(a[6 * t + 4], v2.x, h0); h1 = fma(a[6 * t + 5], v2.y, h1);
         if (lane < NV) sts_f64(ha, h0 + h1);
       }
+    }
+    if (lane < NV) {
+#pragma unroll
+      for (int l = 0; l < 6; ++l) sts_f64(hrow_a + 8 * l, hb[l]);
     }
     __syncwarp();
 

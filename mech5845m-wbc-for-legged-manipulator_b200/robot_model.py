@@ -592,6 +592,26 @@ class RobotModel:
         grip = joint_config[:, 12:]
         return FL_leg, FR_leg, RL_leg, RR_leg, grip
 
+    def rollout(self, target_EE_traj, target_trunk_traj, imu_quat_traj=None, record=False):
+        """Closed-loop horizon (BASELINE config 5): K consecutive runWBC ticks (:1330-1412) for all N robots, one fused
+        launch per tick; task memory and configuration stay resident on the device between ticks.
+
+        ``target_EE_traj`` [K, N, 5, 3], ``target_trunk_traj`` [K, N, 3], optional ``imu_quat_traj`` [K, N, 4] (base
+        orientation fed back each tick; default: the integrated orientation).  Returns qdot of the last tick, or with
+        ``record`` the tuple (q history [K, N, nq], qdot history [K, N, nv], status history [K, N]).
+        """
+        K = int(target_EE_traj.shape[0])
+        qs, vs, st = [], [], []
+        for k in range(K):
+            imu = imu_quat_traj[k] if imu_quat_traj is not None else None
+            self.step(target_EE_traj[k], target_trunk_traj[k], imu_quat=imu, advance=True)
+            if record:
+                qs.append(self.current_joint_config.clone()); vs.append(self.qdot.clone()); st.append(self.last_status.clone())
+        self.firstQP = False
+        if record:
+            return torch.stack(qs), torch.stack(vs), torch.stack(st)
+        return self.qdot
+
     def launch_info(self):
         g, b, s, r = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         cabi.check(self._lib.wbc_step_launch_info(self._model, C.byref(g), C.byref(b), C.byref(s), C.byref(r)))

@@ -222,3 +222,29 @@ def test_config2_every_state_against_the_c_oracle():
         act = robot.last_active_set.cpu().numpy().astype(np.uint64)
         assert (act == ref["active_set"]).all()
         assert np.abs(robot._mem.cpu().numpy() - ref["mem_out"]).max() < 1e-12
+
+
+def test_closed_loop_rollout_matches_oracle():
+    """BASELINE config 5 in miniature: Euler-integrated closed loop (integrate + base estimate + second FK pass,
+    Robot_Wrapper4.py:1397-1402, 1297-1327) over K ticks; every tick's configuration compared with the oracle loop."""
+    name, N, K = "a1_wx200", 24, 8
+    robot = _robot(name, N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260005, 5e-4)
+    rng = np.random.default_rng(5)
+    drift = torch.as_tensor(rng.normal(0, 2e-4, size=(K, N, 18)), device="cuda:0").cumsum(0)   # slowly moving targets
+    traj = targets[None] + drift
+    mem0, ref0 = robot._mem.clone().cpu().numpy(), robot._ref.clone().cpu().numpy()
+    qh, vh, sh = robot.rollout(traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18], record=True)
+    assert (sh == 0).all()
+    qh, vh = qh.cpu().numpy(), vh.cpu().numpy()
+    rm = H.make_oracle(name, like=robot, dt=robot.dt)
+    traj_h = traj.cpu().numpy()
+    worst_q = worst_v = 0.0
+    for s in range(0, N, 3):
+        qs, mem = q[s].copy(), mem0[s].copy()
+        for k in range(K):
+            r = H.oracle_step_one(rm, qs, traj_h[k, s], mem, ref0[s], imu=None, solve=True, tail=True)
+            worst_v = max(worst_v, np.abs(vh[k, s] - r["qdot"]).max())
+            worst_q = max(worst_q, np.abs(qh[k, s] - r["q_next"]).max())
+            qs, mem = r["q_next"], H.get_oracle_mem(rm)
+    assert worst_v < QP_TOL and worst_q < 1e-8, (worst_v, worst_q)
