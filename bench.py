@@ -375,6 +375,12 @@ def run_ours(args):
         ach_tflops = f_step * n_local / kern_s / 1e12
         bytes_state = algorithmic_bytes(table.nq, table.nv)
         info = robot.launch_info()
+        traffic = None                                     # measured DRAM bytes of one launch (ncu), scaled to this launch
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic = tr["bytes_per_state"] * n_local
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -386,7 +392,9 @@ def run_ours(args):
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp64_fma", "achieved": ach_tflops, "peak": peak.value / 1e12, "unit": "TFLOP/s",
-                         "frac": ach_tflops / (peak.value / 1e12), "traffic": None,
+                         "frac": ach_tflops / (peak.value / 1e12), "traffic": traffic,
+                         "traffic_source": "profiles/r1_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of "
+                                           "wbc_step_kernel at 131072 states, per state x states of this launch",
                          "peak_source": "measured in this run: DFMA-saturating microkernel (wbc_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_state": {"fk_jac_targets": f_fkj, "AtA_sym_dense": f_asm, "qp": f_qp, "total": f_step},
