@@ -172,8 +172,47 @@ __device__ __forceinline__ void axis_angle_matrix(const double* a, double s, dou
 }
 
 // --- SciPy Rotation restatements (oracle/rotation_port.py has the same sequences) -----------------
-// Rotation.from_matrix(R).as_quat(), orthogonal R, (x, y, z, w), no sign canonicalisation.
-__device__ __forceinline__ void scipy_quat_from_matrix(const double* R, double* q) {
+// Rotation.from_matrix's pre-step (scipy _rotation_xp.py:51-88): a matrix whose Gramian R R^T is not close to I
+// (isclose with atol 1e-12, rtol 1e-5: 1e-12 off the diagonal, 1e-5 on it) is replaced by its nearest orthogonal
+// matrix U V^T.  The free-flyer FK does not normalise the quaternion (Eigen toRotationMatrix), so this triggers
+// whenever a configuration's quaternion is not unit to ~1e-13 -- e.g. qpJointb "MANI" perturbing the quaternion
+// entries.  U V^T is the polar factor; it is computed by Newton's iteration X <- (X + X^-T) / 2, which converges
+// quadratically to the same matrix the SVD gives.
+__device__ __forceinline__ void scipy_orthogonalize(double* R) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) {
+      const double g = R[3 * i] * R[3 * j] + R[3 * i + 1] * R[3 * j + 1] + R[3 * i + 2] * R[3 * j + 2];
+      ok = ok && ((i == j) ? (fabs(g - 1.0) <= 1e-12 + 1e-5) : (fabs(g) <= 1e-12));
+    }
+  if (ok) return;
+#pragma unroll 1
+  for (int it = 0; it < 30; ++it) {
+    double C[9];                                   // cofactor matrix: X^-T = C / det
+    C[0] = R[4] * R[8] - R[5] * R[7]; C[1] = R[5] * R[6] - R[3] * R[8]; C[2] = R[3] * R[7] - R[4] * R[6];
+    C[3] = R[2] * R[7] - R[1] * R[8]; C[4] = R[0] * R[8] - R[2] * R[6]; C[5] = R[1] * R[6] - R[0] * R[7];
+    C[6] = R[1] * R[5] - R[2] * R[4]; C[7] = R[2] * R[3] - R[0] * R[5]; C[8] = R[0] * R[4] - R[1] * R[3];
+    const double det = R[0] * C[0] + R[1] * C[1] + R[2] * C[2];
+    double change = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double x = 0.5 * (R[i] + C[i] / det);
+      change = fmax(change, fabs(x - R[i]));
+      R[i] = x;
+    }
+    if (change <= 1e-16) break;
+  }
+}
+
+// Rotation.from_matrix(R).as_quat(), (x, y, z, w), no sign canonicalisation; a copy of R is orthogonalised first
+// when SciPy would do so.
+__device__ __forceinline__ void scipy_quat_from_matrix(const double* Rin, double* q) {
+  double R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = Rin[i];
+  scipy_orthogonalize(R);
   const double tr = R[0] + R[4] + R[8];
   int choice = 0;
   double best = R[0];

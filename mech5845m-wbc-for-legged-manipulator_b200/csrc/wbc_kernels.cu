@@ -53,7 +53,7 @@ template <bool SPLIT> struct StepWarps {
   static constexpr int ctas = SPLIT ? WBC_STEP_CTAS : 1;
 };
 
-template <int NV, bool DEBUG_OUT, bool SPLIT>
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD>
 __global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>::ctas) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>
   const StepLayout L = step_layout(NV, P.nC);
   const int warp = threadIdx.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
-  warp_wbc_states<NV, DEBUG_OUT, SPLIT>(P, Ms, ws, L);
+  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD>(P, Ms, ws, L);
 }
 
 // FK + frame Jacobians accessor (HBM-write bound): one state per warp
@@ -436,7 +436,7 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
 
 static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15); }
 
-template <int NV, bool DBG, bool SPLIT>
+template <int NV, bool DBG, bool SPLIT, bool FD>
 static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
   const StepLayout L = step_layout(NV, P.nC);
   const size_t per_warp = (size_t)L.total * sizeof(double);
@@ -447,7 +447,7 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
   if (warps > StepWarps<SPLIT>::value) warps = StepWarps<SPLIT>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
   const size_t smem = model_smem_bytes() + warps * per_warp;
-  auto kern = wbc_step_kernel<NV, DBG, SPLIT>;
+  auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + warps - 1) / warps;
   int grid = (int)(need < (long long)model->sm_count * ctas ? need : (long long)model->sm_count * ctas);
@@ -466,8 +466,13 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
 
 template <int NV, bool DBG>
 static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
-  if (DBG) return launch_step_k<NV, DBG, true>(model, P, st, info);      // the accessor never reaches the solver
-  return P.nC <= 16 ? launch_step_k<NV, DBG, true>(model, P, st, info) : launch_step_k<NV, DBG, false>(model, P, st, info);
+  // FD: the finite-difference joint-task modes ("MANI" / "HYBRID") are their own instantiation
+  const bool fd = (P.cfg.task_mask & WBC_TASK_JOINT) && (P.cfg.joint_mode == WBC_JOINT_MANI || P.cfg.joint_mode == WBC_JOINT_HYBRID);
+  if (DBG)                                                                     // the accessor never reaches the solver
+    return fd ? launch_step_k<NV, DBG, true, true>(model, P, st, info) : launch_step_k<NV, DBG, true, false>(model, P, st, info);
+  if (P.nC <= 16)
+    return fd ? launch_step_k<NV, DBG, true, true>(model, P, st, info) : launch_step_k<NV, DBG, true, false>(model, P, st, info);
+  return fd ? launch_step_k<NV, DBG, false, true>(model, P, st, info) : launch_step_k<NV, DBG, false, false>(model, P, st, info);
 }
 
 template <bool DBG>
@@ -482,8 +487,7 @@ static int launch_step(const WbcModel* model, const StepParams& P, cudaStream_t 
 
 static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, StepParams* P) {
   if (!model || !cfg || !io) return fail(WBC_ERR_INVALID_ARG, "null model / config / io%s");
-  if (cfg->joint_mode == WBC_JOINT_MANI || cfg->joint_mode == WBC_JOINT_HYBRID)
-    if (cfg->task_mask & WBC_TASK_JOINT) return fail(WBC_ERR_UNSUPPORTED, "joint-task modes MANI / HYBRID are not implemented yet%s");
+  if (cfg->joint_mode < WBC_JOINT_ZERO || cfg->joint_mode > WBC_JOINT_HYBRID) return fail(WBC_ERR_INVALID_ARG, "unknown joint_mode%s");
   if (cfg->n_extra_rows < 0 || cfg->n_extra_rows > WBC_MAX_EXTRA_ROWS) return fail(WBC_ERR_INVALID_ARG, "n_extra_rows out of range%s");
   for (int e = 0; e < cfg->n_extra_rows; ++e)
     if (cfg->extra_frame[e] < 0 || cfg->extra_frame[e] >= WBC_HOT_FRAMES) return fail(WBC_ERR_INVALID_ARG, "extra row frame must be a hot frame slot 0..5%s");

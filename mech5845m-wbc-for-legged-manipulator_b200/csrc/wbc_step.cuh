@@ -276,6 +276,152 @@ __device__ __forceinline__ void frame_jac_lwa(const double* S, bool sup, const d
   Jc[3] = S[3]; Jc[4] = S[4]; Jc[5] = S[5];
 }
 
+// column `lane` of data.J (computeJointJacobians, WORLD frame): [lin; ang]
+template <int NV>
+__device__ __forceinline__ void warp_jac_col_a(uint32_t M_a, uint32_t omi_a, int lane, double* Sc) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) Sc[i] = 0.0;
+  if (lane < NV) {
+    const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(col_joint) + 4 * lane);
+    double R[9], axl[3], aw[3];
+    lds_mat3(Ta, R);
+    lds_vec3(M_a + WBC_MOFF(col_axis) + 24 * lane, axl);
+    mat3_vec(R, axl, aw);
+    if (lds_s32(M_a + WBC_MOFF(col_ang) + 4 * lane)) {
+      double p[3];
+      lds_vec3(Ta + 72, p);
+      cross3(p, aw, Sc);
+      Sc[3] = aw[0]; Sc[4] = aw[1]; Sc[5] = aw[2];
+    } else {
+      Sc[0] = aw[0]; Sc[1] = aw[1]; Sc[2] = aw[2];
+    }
+  }
+}
+
+// sqrt(det(J J^T)) of getJointJacobian(joint, LOCAL_WORLD_ALIGNED): the manipulability measure of qpJointb's "MANI" /
+// "HYBRID" modes (Robot_Wrapper4.py:1233-1236).  G_a: [32][6] scratch, Mm_a: [36] scratch.  Uniform result.
+template <int NV>
+__device__ __forceinline__ double warp_manip_a(uint32_t M_a, uint32_t omi_a, uint32_t G_a, uint32_t Mm_a, int jid, int lane) {
+  double Sc[6], Jc[6], pj[3];
+  warp_jac_col_a<NV>(M_a, omi_a, lane, Sc);
+  const uint32_t supp = (uint32_t)lds_s32(M_a + WBC_MOFF(joint_supp) + 4 * jid);
+  lds_vec3(omi_a + 8 * (WBC_T_STRIDE * jid + 9), pj);
+  frame_jac_lwa(Sc, lane < NV && ((supp >> lane) & 1u), pj, false, Jc);
+#pragma unroll
+  for (int r = 0; r < 6; ++r) sts_f64(G_a + 8 * (6 * lane + r), Jc[r]);
+  __syncwarp();
+  if (lane < 21) {                       // upper triangle of the 6 x 6 Gram matrix, one entry per lane
+    int r = 0, rem = lane;
+    while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+    const int c = r + rem;
+    double acc = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < NV; ++k) acc = fma(lds_f64(G_a + 8 * (6 * k + r)), lds_f64(G_a + 8 * (6 * k + c)), acc);
+    sts_f64(Mm_a + 8 * (6 * r + c), acc);
+    sts_f64(Mm_a + 8 * (6 * c + r), acc);
+  }
+  __syncwarp();
+  double f = 0.0;
+  if (lane == 0) {                       // determinant by LU with partial pivoting (np.linalg.det)
+    double det = 1.0;
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) {
+      int piv = k;
+      double best = fabs(lds_f64(Mm_a + 8 * (6 * k + k)));
+#pragma unroll 1
+      for (int i = k + 1; i < 6; ++i) {
+        const double v = fabs(lds_f64(Mm_a + 8 * (6 * i + k)));
+        if (v > best) { best = v; piv = i; }
+      }
+      if (piv != k) {
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          const double t0 = lds_f64(Mm_a + 8 * (6 * k + c)), t1 = lds_f64(Mm_a + 8 * (6 * piv + c));
+          sts_f64(Mm_a + 8 * (6 * k + c), t1);
+          sts_f64(Mm_a + 8 * (6 * piv + c), t0);
+        }
+        det = -det;
+      }
+      const double d = lds_f64(Mm_a + 8 * (6 * k + k));
+      det *= d;
+      if (d == 0.0) break;
+#pragma unroll 1
+      for (int i = k + 1; i < 6; ++i) {
+        const double l = lds_f64(Mm_a + 8 * (6 * i + k)) / d;
+#pragma unroll 1
+        for (int c = k + 1; c < 6; ++c)
+          sts_f64(Mm_a + 8 * (6 * i + c), lds_f64(Mm_a + 8 * (6 * i + c)) - l * lds_f64(Mm_a + 8 * (6 * k + c)));
+      }
+    }
+    f = sqrt(det);
+  }
+  __syncwarp();
+  return __shfl_sync(WBC_FULL_MASK, f, 0);
+}
+
+// updateState (Robot_Wrapper4.py:387-428) for one state: forwardKinematics into oMi, column `lane` of the WORLD joint
+// Jacobian (computeJointJacobians), the six hot frame placements (updateFramePlacements) and, when the CoM constraint
+// is on, the centre of mass and column `lane` of jacobianCenterOfMass (rows x, y).
+template <int NV>
+__device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t omi_a, uint32_t omf_a, int lane, bool com_on,
+                                           double* Sc, double* com_w, double* Jcom) {
+  warp_fk_a(M_a, q_a, omi_a, lane);
+  warp_jac_col_a<NV>(M_a, omi_a, lane, Sc);
+  if (lane < WBC_HOT_FRAMES) {         // hot frames: 5 EE + trunk
+    const uint32_t Pa = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(frame_parent) + 4 * lane);
+    double Rp[9], R[9], p[3], fp[3], pp[3];
+    lds_mat3(Pa, Rp);
+    lds_vec3(Pa + 72, pp);
+    lds_vec3(M_a + WBC_MOFF(frp) + 24 * lane, fp);
+    if (lds_s32(M_a + WBC_MOFF(fr_ident) + 4 * lane)) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = Rp[i];
+    } else {
+      double FR[9];
+      lds_mat3(M_a + WBC_MOFF(frR) + 72 * lane, FR);
+      mat3_mul(Rp, FR, R);
+    }
+    mat3_vec(Rp, fp, p);
+    const uint32_t oa = omf_a + 8 * WBC_T_STRIDE * lane;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sts_f64(oa + 8 * i, R[i]);
+    sts_f64(oa + 72, p[0] + pp[0]); sts_f64(oa + 80, p[1] + pp[1]); sts_f64(oa + 88, p[2] + pp[2]);
+  }
+  // centre of mass (only when the CoM constraint is on): lane j -> m_j * c_j in the world
+  com_w[0] = com_w[1] = com_w[2] = 0.0;
+  Jcom[0] = Jcom[1] = 0.0;
+  if (com_on) {
+    double mc[4] = {0, 0, 0, 0};
+    const int nj = lds_s32(M_a + WBC_MOFF(njoints));
+    if (lane >= 1 && lane < nj) {
+      const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lane;
+      double R[9], c[3], cl[3], pj[3];
+      lds_mat3(Ta, R);
+      lds_vec3(Ta + 72, pj);
+      lds_vec3(M_a + WBC_MOFF(com) + 24 * lane, cl);
+      mat3_vec(R, cl, c);
+      const double m = lds_f64(M_a + WBC_MOFF(mass) + 8 * lane);
+      mc[0] = m; mc[1] = m * (c[0] + pj[0]); mc[2] = m * (c[1] + pj[1]); mc[3] = m * (c[2] + pj[2]);
+    }
+    // subtree sums for my column: sum over joints j in sub_joints[lane]
+    double sm = 0, s1 = 0, s2 = 0, s3 = 0;
+    const uint32_t sub = (lane < NV) ? (uint32_t)lds_s32(M_a + WBC_MOFF(sub_joints) + 4 * lane) : 0u;
+    for (int j = 1; j < nj; ++j) {
+      const double m0 = __shfl_sync(WBC_FULL_MASK, mc[0], j), m1 = __shfl_sync(WBC_FULL_MASK, mc[1], j);
+      const double m2 = __shfl_sync(WBC_FULL_MASK, mc[2], j), m3 = __shfl_sync(WBC_FULL_MASK, mc[3], j);
+      if ((sub >> j) & 1u) { sm += m0; s1 += m1; s2 += m2; s3 += m3; }
+    }
+    const double Mt = lds_f64(M_a + WBC_MOFF(total_mass));
+    com_w[0] = warp_sum(mc[1]) / Mt; com_w[1] = warp_sum(mc[2]) / Mt; com_w[2] = warp_sum(mc[3]) / Mt;
+    // Jcom column = (sm * lin - (sum m c) x ang) / M   (only x, y rows are used, :670)
+    const double msc[3] = {s1, s2, s3};
+    double cx[3];
+    cross3(msc, Sc + 3, cx);
+    Jcom[0] = (sm * Sc[0] - cx[0]) / Mt;
+    Jcom[1] = (sm * Sc[1] - cx[1]) / Mt;
+  }
+}
+
 template <bool ON>
 __device__ __forceinline__ void phase_sync() {
   if (ON) __syncthreads();
@@ -292,7 +438,7 @@ __device__ __forceinline__ void phase_sync() {
 // apart each stream the whole code from L2 on their own (measured: 2.4x slower without the barriers); in step,
 // one fetch feeds all warps.  Padding warps shadow the last state (no writes) so the barriers stay uniform.
 // Shared memory is addressed through 32-bit shared-window addresses (wbc_device.cuh: smem_addr, lds_*, sts_*).
-template <int NV, bool DEBUG_OUT, bool SPLIT>
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD>
 __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws, const StepLayout L) {
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
   constexpr int LD = NV | 1;
@@ -346,78 +492,9 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     phase_sync<PS>();
 
     // ---------------------------------------------------------------- kinematics
-    warp_fk_a(M_a, q_a, omi_a, lane);
     double Sc[6];                        // column `lane` of data.J (WORLD): [lin; ang]
-#pragma unroll
-    for (int i = 0; i < 6; ++i) Sc[i] = 0.0;
-    if (lane < NV) {
-      const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(col_joint) + 4 * lane);
-      double R[9], axl[3], aw[3];
-      lds_mat3(Ta, R);
-      lds_vec3(M_a + WBC_MOFF(col_axis) + 24 * lane, axl);
-      mat3_vec(R, axl, aw);
-      if (lds_s32(M_a + WBC_MOFF(col_ang) + 4 * lane)) {
-        double p[3];
-        lds_vec3(Ta + 72, p);
-        cross3(p, aw, Sc);
-        Sc[3] = aw[0]; Sc[4] = aw[1]; Sc[5] = aw[2];
-      } else {
-        Sc[0] = aw[0]; Sc[1] = aw[1]; Sc[2] = aw[2];
-      }
-    }
-    if (lane < WBC_HOT_FRAMES) {         // hot frames: 5 EE + trunk
-      const uint32_t Pa = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(frame_parent) + 4 * lane);
-      double Rp[9], R[9], p[3], fp[3], pp[3];
-      lds_mat3(Pa, Rp);
-      lds_vec3(Pa + 72, pp);
-      lds_vec3(M_a + WBC_MOFF(frp) + 24 * lane, fp);
-      if (lds_s32(M_a + WBC_MOFF(fr_ident) + 4 * lane)) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) R[i] = Rp[i];
-      } else {
-        double FR[9];
-        lds_mat3(M_a + WBC_MOFF(frR) + 72 * lane, FR);
-        mat3_mul(Rp, FR, R);
-      }
-      mat3_vec(Rp, fp, p);
-      const uint32_t oa = omf_a + 8 * WBC_T_STRIDE * lane;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) sts_f64(oa + 8 * i, R[i]);
-      sts_f64(oa + 72, p[0] + pp[0]); sts_f64(oa + 80, p[1] + pp[1]); sts_f64(oa + 88, p[2] + pp[2]);
-    }
-    // centre of mass (only when the CoM constraint is on): lane j -> m_j * c_j in the world
-    double com_w[3] = {0, 0, 0};
-    double Jcom[2] = {0, 0};
-    if (cfg.constraint_mask & WBC_CON_COM) {
-      double mc[4] = {0, 0, 0, 0};
-      const int nj = lds_s32(M_a + WBC_MOFF(njoints));
-      if (lane >= 1 && lane < nj) {
-        const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lane;
-        double R[9], c[3], cl[3], pj[3];
-        lds_mat3(Ta, R);
-        lds_vec3(Ta + 72, pj);
-        lds_vec3(M_a + WBC_MOFF(com) + 24 * lane, cl);
-        mat3_vec(R, cl, c);
-        const double m = lds_f64(M_a + WBC_MOFF(mass) + 8 * lane);
-        mc[0] = m; mc[1] = m * (c[0] + pj[0]); mc[2] = m * (c[1] + pj[1]); mc[3] = m * (c[2] + pj[2]);
-      }
-      // subtree sums for my column: sum over joints j in sub_joints[lane]
-      double sm = 0, s1 = 0, s2 = 0, s3 = 0;
-      const uint32_t sub = (lane < NV) ? (uint32_t)lds_s32(M_a + WBC_MOFF(sub_joints) + 4 * lane) : 0u;
-      for (int j = 1; j < nj; ++j) {
-        const double m0 = __shfl_sync(WBC_FULL_MASK, mc[0], j), m1 = __shfl_sync(WBC_FULL_MASK, mc[1], j);
-        const double m2 = __shfl_sync(WBC_FULL_MASK, mc[2], j), m3 = __shfl_sync(WBC_FULL_MASK, mc[3], j);
-        if ((sub >> j) & 1u) { sm += m0; s1 += m1; s2 += m2; s3 += m3; }
-      }
-      const double Mt = lds_f64(M_a + WBC_MOFF(total_mass));
-      com_w[0] = warp_sum(mc[1]) / Mt; com_w[1] = warp_sum(mc[2]) / Mt; com_w[2] = warp_sum(mc[3]) / Mt;
-      // Jcom column = (sm * lin - (sum m c) x ang) / M   (only x, y rows are used, :670)
-      const double msc[3] = {s1, s2, s3};
-      double cx[3];
-      cross3(msc, Sc + 3, cx);
-      Jcom[0] = (sm * Sc[0] - cx[0]) / Mt;
-      Jcom[1] = (sm * Sc[1] - cx[1]) / Mt;
-    }
+    double com_w[3], Jcom[2];
+    warp_kin_a<NV>(M_a, q_a, omi_a, omf_a, lane, (cfg.constraint_mask & WBC_CON_COM) != 0, Sc, com_w, Jcom);
     phase_sync<PS>();
 
     // ---------------------------------------------------------------- task rows for my column (registers)
@@ -555,12 +632,85 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       sts_f64(cub_a + 8 * (row_extra + lane), cfg.extra_hi[lane]);
     }
 
+    // ---------------------------------------------------------------- qpJointb "MANI" / "HYBRID" (:1219-1260)
+    // Central finite differences of the manipulability sqrt(det(J J^T)) of one joint Jacobian per probed DoF: two
+    // extra FK passes each.  Reference quirks kept: the configuration is indexed with the velocity
+    // index, the perturbations accumulate (each probed entry ends at q - dq), and the perturbed state is what the
+    // constraint rows, the bounds and the integration that follow see (A and the Cartesian targets were taken before).
+    double u_fd = 0.0;
+    const bool fd_on = FD && joint_on && (cfg.joint_mode == WBC_JOINT_MANI || cfg.joint_mode == WBC_JOINT_HYBRID);
+    if (FD && fd_on) {                                               // FD: separate kernel instantiation, so the
+                                                                     // common modes do not carry its register pressure
+      const bool mani = cfg.joint_mode == WBC_JOINT_MANI;
+      const uint32_t G_a = ast_a, Mm_a = ast_a + 8 * 192, qp_a = ast_a + 8 * 232;   // AsT is not written yet
+      const double deltaq = 0.0002;
+      for (int i = lane; i < nq; i += 32) sts_f64(qp_a + 8 * i, lds_f64(q_a + 8 * i));
+      if (!mani && lane < NV) u_fd = lds_f64(q_a + 8 * ((lane < 6) ? lane : lane + 1));   // u = np.delete(q, 6)
+      __syncwarp();
+      bool any = false;
+#pragma unroll 1
+      for (int i = 0; i < NV; ++i) {
+        const int jid = mani ? (i < 6 ? 1 : i + 1 - 5) : (i - 6);
+        if (!mani && jid < cfg.arm_base_id) continue;
+        any = true;
+        double f1 = 0.0, f2 = 0.0;
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+          if (lane == 0) {
+            const double qi = lds_f64(qp_a + 8 * i);
+            sts_f64(qp_a + 8 * i, side == 0 ? qi + deltaq : qi - (deltaq * 2));
+          }
+          __syncwarp();
+          warp_fk_a(M_a, qp_a, omi_a, lane);
+          const double f = warp_manip_a<NV>(M_a, omi_a, G_a, Mm_a, jid, lane);
+          if (side == 0) f1 = f; else f2 = f;
+        }
+        if (lane == i) u_fd = 0.5 * (f1 - f2) / deltaq;
+      }
+      if (any) {          // current_joint_config is the perturbed array from here on: refresh what depends on it
+        for (int i = lane; i < nq; i += 32) sts_f64(q_a + 8 * i, lds_f64(qp_a + 8 * i));
+        __syncwarp();
+        warp_kin_a<NV>(M_a, q_a, omi_a, omf_a, lane, (cfg.constraint_mask & WBC_CON_COM) != 0, Sc, com_w, Jcom);
+        if (row_trunk >= 0 && lane == WBC_FRAME_TRUNK) {             // trunkConstraint (:707-754) at the perturbed state
+          const uint32_t T_a = omf_a + 8 * WBC_T_STRIDE * WBC_FRAME_TRUNK;
+          double Rf[9], fq[4], eul[3], ip[3], ie[3];
+          lds_mat3(T_a, Rf);
+          scipy_quat_from_matrix(Rf, fq);
+          scipy_euler_xyz_from_quat(fq, eul);
+          lds_vec3(ref_a + 8 * REF_INIT_TRUNK_POS, ip);
+          lds_vec3(ref_a + 8 * REF_INIT_TRUNK_EUL, ie);
+          const double cur[4] = {lds_f64(T_a + 88), eul[0], eul[1], eul[2]};
+          const double z_var = ip[2] * 0.25;
+          const double var = 1.5 * 0.1;
+          const double lo[4] = {ip[2] - z_var, ie[0] - var, ie[1] - var, ie[2] - var};
+          const double up[4] = {ip[2] + z_var, ie[0] + var, ie[1] + var, ie[2] + var};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            sts_f64(clb_a + 8 * (row_trunk + r), ((lo[r] - cur[r]) * inv_dt) * 0.5);
+            sts_f64(cub_a + 8 * (row_trunk + r), ((up[r] - cur[r]) * inv_dt) * 0.5);
+          }
+        }
+        if (row_com >= 0 && lane == 0) {
+          double FL[3], RR[3];
+          lds_vec3(omf_a + 8 * (1 * WBC_T_STRIDE + 9), FL);
+          lds_vec3(omf_a + 8 * (2 * WBC_T_STRIDE + 9), RR);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            sts_f64(clb_a + 8 * (row_com + r), ((RR[r] - com_w[r]) * inv_dt) * 0.8);
+            sts_f64(cub_a + 8 * (row_com + r), ((FL[r] - com_w[r]) * inv_dt) * 0.8);
+          }
+        }
+        __syncwarp();
+      }
+    }
+
     // ---------------------------------------------------------------- box bounds, joint task
     double lbv = 0.0, ubv = 0.0;
     if (lane < NV) damper_bounds_a(M_a, cfg, q_a, lane, lbv, ubv);
     double bj = 0.0;
     if (joint_on && cfg.joint_mode == WBC_JOINT_PREV && lane < NV)               // qpJointb "PREV" (:1216-1217)
       bj = ((1.0 / NV) * lds_f64(q_a + 8 * ((lane < 6) ? lane : lane + 1))) * cfg.joint_task_weight;
+    if (fd_on && lane < NV) bj = ((1.0 / NV) * u_fd) * cfg.joint_task_weight;
 
     // ---------------------------------------------------------------- H = A^T A, g = -A^T b
     // Column `lane` of the 36 Cartesian rows goes to shared memory transposed (AsT[lane][r]); then for every

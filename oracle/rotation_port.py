@@ -15,8 +15,26 @@ import math
 import numpy as np
 
 
+def orthogonalize(R):
+    """from_matrix's pre-step: nearest orthogonal matrix U V^T when R R^T is not close to I (atol 1e-12 off the diagonal,
+    1e-12 + 1e-5 on it); Newton's polar iteration X <- (X + X^-T) / 2, the sequence the CUDA device function follows."""
+    R = np.array(R, dtype=float)
+    G = R @ R.T
+    ok = all((abs(G[i, j] - 1.0) <= 1e-12 + 1e-5) if i == j else (abs(G[i, j]) <= 1e-12) for i in range(3) for j in range(i, 3))
+    if ok:
+        return R
+    for _ in range(30):
+        X = 0.5 * (R + np.linalg.inv(R).T)
+        change = np.abs(X - R).max()
+        R = X
+        if change <= 1e-16:
+            break
+    return R
+
+
 def quat_from_matrix(R):
-    """Rotation.from_matrix(R).as_quat() for an orthogonal R (no sign canonicalisation)."""
+    """Rotation.from_matrix(R).as_quat() (no sign canonicalisation); R is orthogonalised first when SciPy would."""
+    R = orthogonalize(R)
     tr = R[0][0] + R[1][1] + R[2][2]
     dec = [R[0][0], R[1][1], R[2][2], tr]
     choice = 0

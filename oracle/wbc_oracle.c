@@ -85,7 +85,34 @@ static void axis_angle(const double* a, double s, double c, double* R) {
 }
 
 /* ---- SciPy Rotation restatements (oracle/rotation_port.py) -------------------------------------- */
-static void sp_quat_from_matrix(const double* R, double* q) {
+/* from_matrix's pre-step: nearest orthogonal matrix when R R^T is not close to I (Newton's polar iteration) */
+static void sp_orthogonalize(double* R) {
+  int ok = 1;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i; j < 3; ++j) {
+      const double g = R[3 * i] * R[3 * j] + R[3 * i + 1] * R[3 * j + 1] + R[3 * i + 2] * R[3 * j + 2];
+      ok = ok && ((i == j) ? (fabs(g - 1.0) <= 1e-12 + 1e-5) : (fabs(g) <= 1e-12));
+    }
+  if (ok) return;
+  for (int it = 0; it < 30; ++it) {
+    double C[9];
+    C[0] = R[4] * R[8] - R[5] * R[7]; C[1] = R[5] * R[6] - R[3] * R[8]; C[2] = R[3] * R[7] - R[4] * R[6];
+    C[3] = R[2] * R[7] - R[1] * R[8]; C[4] = R[0] * R[8] - R[2] * R[6]; C[5] = R[1] * R[6] - R[0] * R[7];
+    C[6] = R[1] * R[5] - R[2] * R[4]; C[7] = R[2] * R[3] - R[0] * R[5]; C[8] = R[0] * R[4] - R[1] * R[3];
+    const double det = R[0] * C[0] + R[1] * C[1] + R[2] * C[2];
+    double change = 0.0;
+    for (int i = 0; i < 9; ++i) {
+      const double x = 0.5 * (R[i] + C[i] / det);
+      if (fabs(x - R[i]) > change) change = fabs(x - R[i]);
+      R[i] = x;
+    }
+    if (change <= 1e-16) break;
+  }
+}
+static void sp_quat_from_matrix(const double* Rin, double* q) {
+  double R[9];
+  memcpy(R, Rin, sizeof(R));
+  sp_orthogonalize(R);
   const double tr = R[0] + R[4] + R[8];
   const double dec[4] = {R[0], R[4], R[8], tr};
   int choice = 0;

@@ -101,9 +101,12 @@ def test_golden_jacobians_neutral_wx200():
     ("a1_px100_pin_ver", P2_TASKS, P2_CONS, "PREV", 5e-4),    # P2 sim3 tick pattern
     ("a1_wx200", P1_TASKS, P2_CONS, True, 5e-3),              # P3 full stack + constraints (stress sigma)
     ("a1_wx200", P1_TASKS, P2_CONS, True, 5e-4),              # P3 nominal sigma
+    ("a1_px100_pin_ver", P2_TASKS, P2_CONS, "HYBRID", 5e-4),  # what sim3.py:145 actually runs (f2): FD manipulability gradient
+    ("a1_wx200", P1_TASKS, P2_CONS, "HYBRID", 5e-4),
+    ("a1_wx200", P2_TASKS, P2_CONS, "MANI", 5e-4),
 ])
 def test_assembly_and_qp_match_oracle(name, tasks, cons, joint, sigma):
-    N = 96
+    N = 96 if joint in (True, "PREV") else (32 if joint == "HYBRID" else 12)    # the FD modes cost 12 / 52 oracle FK passes per state
     robot = _robot(name, N, tasks, cons, joint)
     q, targets = _load(robot, N, 20260002, sigma)
     mem0, ref0 = robot._mem.clone(), robot._ref.clone()

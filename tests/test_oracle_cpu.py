@@ -210,6 +210,12 @@ def test_rotation_port_matches_scipy():
         q2 = rp.quat_from_matrix(M)
         qs2 = R.from_matrix(M).as_quat()
         assert np.abs(q2 - qs2).max() < 1e-12 or np.abs(q2 + qs2).max() < 1e-12
+        # non-unit quaternion through the free-flyer FK (Eigen toRotationMatrix, no normalisation): SciPy projects the
+        # non-orthogonal matrix onto the nearest rotation (U V^T); the port follows with Newton's polar iteration
+        qn = q * (1.0 + rng.uniform(-3e-4, 3e-4))
+        Mn = np.array(opin.quat_to_matrix(*qn)).reshape(3, 3)
+        q3, qs3 = rp.quat_from_matrix(Mn), R.from_matrix(Mn).as_quat()
+        assert np.abs(q3 - qs3).max() < 1e-12 or np.abs(q3 + qs3).max() < 1e-12
 
 
 # ------------------------------------------------------------------------------------------------ QP
