@@ -251,3 +251,41 @@ def test_closed_loop_rollout_matches_oracle():
             worst_q = max(worst_q, np.abs(qh[k, s] - r["q_next"]).max())
             qs, mem = r["q_next"], H.get_oracle_mem(rm)
     assert worst_v < QP_TOL and worst_q < 1e-8, (worst_v, worst_q)
+
+
+def test_config3_extension_rows_full_size():
+    """BASELINE config 3: A1 + WX200, 65,536 states, friction-pyramid style rows through the generic extension-row
+    channel (NOT in the reference: parity unpinned by construction; the C oracle implements the same channel).
+    20 constraint rows exercise the full-width (nC > 16) solver layout.  Size-independent properties on every state,
+    solutions of the first 2048 states against the C oracle."""
+    import wbc_b200
+    from oracle import c_port
+    N, mu, big = 65536, 0.6, 1e30
+    robot = _robot("a1_wx200", N, P1_TASKS, dict(CoM=False, Trunk=True, FR=False, FL=False, RR=False, RL=False, Grip=False), True)
+    rows = []
+    for foot in range(4):                      # foot velocity v (LOCAL_WORLD_ALIGNED): +-v_x - mu v_z <= 0, +-v_y - mu v_z <= 0
+        for cx, cy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            rows.append((foot, wbc_b200._cabi.RF_LOCAL_WORLD_ALIGNED, [cx, cy, -mu, 0, 0, 0], -big, 0.0))
+    robot.extra_rows = rows
+    q, targets = _load(robot, N, 20260003, 5e-3)
+    mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+    asm = robot.assemble(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], want=("C", "Clb", "Cub", "lb", "ub"))
+    assert asm["C"].shape[1] == 20
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=False)
+    assert (robot.last_status == 0).all()
+    Cx = torch.einsum("nrk,nk->nr", asm["C"], x)
+    assert (Cx >= asm["Clb"] - 1e-7).all() and (Cx <= asm["Cub"] + 1e-7).all()
+    assert (x >= asm["lb"] - 1e-9).all() and (x <= asm["ub"] + 1e-9).all()
+    assert float((robot.last_active_set[:, 1] != 0).double().mean()) > 0.05      # the pyramid rows do bind
+    n = 2048
+    ts, table = c_port.table_struct("a1_wx200")
+    ref = c_port.step(ts, c_port.config_struct(robot, table), q[:n], targets[:n].cpu().numpy(), mem0[:n].cpu().numpy(),
+                      ref0[:n].cpu().numpy(), robot.dt)
+    assert (ref["status"] == 0).all()
+    assert np.abs(x[:n].cpu().numpy() - ref["qdot"]).max() < QP_TOL
+    # the pyramid rows come in mirrored pairs, so "most violated" ties are common and the incremental C x of the kernel
+    # may break one differently from the oracle's fresh product: the minimiser is the same, the path occasionally not
+    same_path = robot.last_iters[:n].cpu().numpy() == ref["iters"]
+    same_set = (robot.last_active_set[:n].cpu().numpy().astype(np.uint64) == ref["active_set"]).all(axis=1)
+    print("config3: identical pivoting path", same_path.mean(), "identical active set", same_set.mean())
+    assert same_path.mean() > 0.97 and same_set.mean() > 0.90      # measured on B200: 0.992 / 0.950 (degenerate vertices)
