@@ -388,7 +388,8 @@ def run_ours(args):
             "p50_step_us": float(np.median(per_step_ms) * 1e3),
             "ns_per_state": 1e6 * total_ms_max / args.steps / n_global * world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "RobotModel.step_host -> wbc_step (C ABI), pinned host buffers"},
+                    "steps": e2e_steps, "api": "RobotModel.step_host -> wbc_step (C ABI): pinned host buffers, 8 slices pipelined "
+                                                  "over 3 streams (H2D | kernel | D2H overlap)", "gpu_launches_per_step": 8},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp64_fma", "achieved": ach_tflops, "peak": peak.value / 1e12, "unit": "TFLOP/s",

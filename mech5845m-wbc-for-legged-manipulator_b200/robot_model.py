@@ -557,25 +557,55 @@ class RobotModel:
             self.current_joint_config = q_next
         return self.qdot
 
-    def step_host(self, host_in, host_out):
+    def step_host(self, host_in, host_out, chunks=8):
         """The fused tick with HOST buffers (what a caller holding NumPy arrays pays end to end).
 
         ``host_in``: dict of pinned float64 CPU tensors q [N, nq], targets [N, 18], mem [N, 72], ref [N, 24];
         ``host_out``: dict of pinned CPU tensors qdot [N, nv], status [N] (int32), iters [N] (int32).
-        Copies host -> device, launches the fused kernel, copies the results back, all on the current stream.
-        Returns (h2d_bytes, d2h_bytes).
+        The batch is cut into ``chunks`` contiguous slices that go host -> device, through the fused kernel and back
+        on three side streams, so the PCIe copies of one slice overlap the kernel of another; the current stream
+        waits for all of them.  Returns (h2d_bytes, d2h_bytes).
         """
-        self.current_joint_config.copy_(host_in["q"], non_blocking=True)
-        self._targets.copy_(host_in["targets"], non_blocking=True)
-        self._mem.copy_(host_in["mem"], non_blocking=True)
-        self._ref.copy_(host_in["ref"], non_blocking=True)
+        N = self.N
         cfg = self._config()
-        io = self._io(targets=self._targets, qdot=self.qdot, status=self.last_status, iters=self.last_iters)
+        cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_side_streams"):
+            self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        chunks = max(1, min(int(chunks), N))
+        bounds = [(N * c) // chunks for c in range(chunks + 1)]
+        dev_in = {"q": self.current_joint_config, "targets": self._targets, "mem": self._mem, "ref": self._ref}
+        dev_out = {"qdot": self.qdot, "status": self.last_status, "iters": self.last_iters}
+        start = torch.cuda.Event()
+        start.record(cur)
+        done = []
         with torch.cuda.device(self.device):
-            cabi.check(self._lib.wbc_step(self._model, C.byref(cfg), C.byref(io), self.N, _stream_ptr()))
-        host_out["qdot"].copy_(self.qdot, non_blocking=True)
-        host_out["status"].copy_(self.last_status, non_blocking=True)
-        host_out["iters"].copy_(self.last_iters, non_blocking=True)
+            for c in range(chunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                if hi == lo:
+                    continue
+                st = self._side_streams[c % len(self._side_streams)]
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    for k in dev_in:
+                        dev_in[k][lo:hi].copy_(host_in[k][lo:hi], non_blocking=True)
+                    io = cabi.WbcStepIO()
+                    io.q = dev_in["q"][lo:hi].data_ptr()
+                    io.targets = dev_in["targets"][lo:hi].data_ptr()
+                    io.mem_in = dev_in["mem"][lo:hi].data_ptr()
+                    io.ref = dev_in["ref"][lo:hi].data_ptr()
+                    io.dt = float(self.dt)
+                    io.qdot = dev_out["qdot"][lo:hi].data_ptr()
+                    io.status = dev_out["status"][lo:hi].data_ptr()
+                    io.iters = dev_out["iters"][lo:hi].data_ptr()
+                    cabi.check(self._lib.wbc_step(self._model, C.byref(cfg), C.byref(io), hi - lo,
+                                                  C.c_void_p(st.cuda_stream)))
+                    for k in dev_out:
+                        host_out[k][lo:hi].copy_(dev_out[k][lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    done.append(ev)
+        for ev in done:
+            cur.wait_event(ev)
         h2d = sum(host_in[k].numel() * 8 for k in ("q", "targets", "mem", "ref"))
         d2h = host_out["qdot"].numel() * 8 + host_out["status"].numel() * 4 + host_out["iters"].numel() * 4
         return h2d, d2h
