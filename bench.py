@@ -346,6 +346,27 @@ def run_ours(args):
     e2e_value = n_global * e2e_steps / (float(t.item()) * 1e-3)
     e2e_ok = bool((host_out["status"] == 0).all().item())
 
+    # ---- single-state latency: one robot, one launch (the reference's own use case: a 500 Hz control tick) ----
+    lat_us = None
+    if rank == 0:
+        one = wbc_b200.RobotModel(args.robot, batch=1, device=dev, dt=args.dt)
+        one.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
+        one.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+        one.current_joint_config.copy_(robot.current_joint_config[:1]); one._mem.copy_(mem0[:1]); one._ref.copy_(robot._ref[:1])
+        t1 = targets[:1].clone()
+        cfg1 = one._config()
+        io1 = one._io(targets=t1, qdot=one.qdot, status=one.last_status, iters=one.last_iters)
+        lib = cabi.load()
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(20):
+            lib.wbc_step(one._model, C.byref(cfg1), C.byref(io1), 1, sp)
+        torch.cuda.synchronize()
+        evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+        for a_, b_ in evl:
+            a_.record(); lib.wbc_step(one._model, C.byref(cfg1), C.byref(io1), 1, sp); b_.record()
+        torch.cuda.synchronize()
+        lat_us = float(np.median([a_.elapsed_time(b_) for a_, b_ in evl]) * 1e3)
+
     # ---- verification gather (off the timed path): NCCL all_gather of solutions / status -------------
     verified = status_ok and e2e_ok
     checksum = float(robot.qdot.double().abs().sum().item())
@@ -387,6 +408,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_local),
             "p50_step_us": float(np.median(per_step_ms) * 1e3),
             "ns_per_state": 1e6 * total_ms_max / args.steps / n_global * world,
+            "p50_single_state_step_us": lat_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "RobotModel.step_host -> wbc_step (C ABI): pinned host buffers, 8 slices pipelined "
                                                   "over 3 streams (H2D | kernel | D2H overlap)", "gpu_launches_per_step": 8},

@@ -72,6 +72,24 @@ class _Data:
         self.oMi = _JointAccessor(owner)
 
 
+class LinearTrajectory:
+    """Batched ``klampt.model.trajectory.Trajectory(milestones=...)`` as the drivers use it (``sim3.py:207-228``,
+    Robot_Wrapper4.py:264-283): piecewise linear, knot i at t = i, clamped at both ends.  ``milestones`` [K, N, 3]."""
+
+    def __init__(self, milestones):
+        self.m = milestones
+
+    def eval(self, t):
+        K = self.m.shape[0]
+        if t <= 0:
+            return self.m[0].clone()
+        if t >= K - 1:
+            return self.m[-1].clone()
+        i = int(np.floor(t))
+        u = t - i
+        return self.m[i] + u * (self.m[i + 1] - self.m[i])
+
+
 class RobotModel:
     def __init__(self, urdf_path, mesh_dir_path=None, EE_frame_names=EE_FRAME_NAMES, EE_joint_names=EE_JOINT_NAMES,
                  G_base="waist", imu="imu_joint", FR_hip_joint="FR_hip_joint",
@@ -434,6 +452,56 @@ class RobotModel:
                                             int(reference_frame), _ptr(oMf), _ptr(J), _stream_ptr()))
         return oMf, J
 
+    # ---------------------------------------------------------------------------------- bootstrap :196-351
+    def setInitialState(self, bootstrap_steps=None):
+        """The reference's constructor bootstrap (Robot_Wrapper4.py:196-351), batched: from ``pin.neutral`` every robot
+        follows linear end-effector trajectories into the crouched start pose with 2000 bounds-only QP ticks (task
+        stack P1, cold QP each tick, plain ``integrate``), one fused launch per tick for the whole batch."""
+        t, N, nq, nv = self.robot_model, self.N, self.n_configuration_dimensions, self.n_velocity_dimensions
+        f64 = dict(dtype=torch.float64, device=self.device)
+        q = torch.zeros(N, nq, **f64)
+        q[:, 6] = 1.0                                                                    # pin.neutral (:199)
+        upper = torch.as_tensor(np.asarray(t.upper, dtype=np.float64)[:nq], **f64)
+        q[:, :nv] = torch.minimum(q[:, :nv], upper[:nv])                                 # :201-208 (quirk D.12: range(nv), upper side only)
+        self.updateState(q, feedback=False)
+        mem, ref = self._log_previous_states()                                           # :214-219
+        self._mem.copy_(mem)
+        self._ref[:, :18] = ref[:, :18]                                                  # default orientations :222-226
+        trunk_target = self.trunk_frame_pos.clone()                                      # :229
+        ee0 = [self.EE_frame_pos[i].clone() for i in range(5)]
+        scale_F = torch.tensor([1.0, 1.0, 0.9], **f64)
+        scale_G = torch.tensor([1.1, 1.0, 1.5], **f64)
+        second = []
+        for i in range(4):                                                               # :247-250
+            p2 = ee0[i].clone()
+            p2[:, 0] = self.robot_data.oMf[self.hip_waist_joint_index_list_frame[i]].translation[:, 0]
+            second.append(p2 * scale_F)
+        g2 = ee0[4].clone()
+        g2[:, 2] = self.robot_data.oMi[self.arm_base_id].translation[:, 2]                # :253
+        g2[:, 0] = self.robot_data.oMi[self.FR_hip_joint].translation[:, 0]               # :254
+        second.append(g2 * scale_G)
+        traj = [LinearTrajectory(torch.stack((ee0[i], second[i]))) for i in range(5)]    # order FR, FL, RR, RL, G (:269)
+        self.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)   # :272
+        ticks = np.arange(0, 2, 0.001).tolist()                                          # :275
+        if bootstrap_steps is not None:
+            ticks = ticks[:bootstrap_steps]
+        was_initialised, self.initialised = self.initialised, False
+        for tt in ticks:                                                                 # :278-325
+            ee = torch.stack([traj[i].eval(tt) for i in range(5)], dim=1)
+            self.step(ee, trunk_target, advance=True, plain_integrate=True, constraint_mask=0)
+        q = self.current_joint_config.clone()
+        q[:, 3:6] = 0.0                                                                  # :328-330
+        self.updateState(q, feedback=False)
+        feet_z = sum(self.EE_frame_pos[i][:, 2] for i in range(4))
+        q = self.current_joint_config.clone()
+        q[:, 2] = -feet_z / 4 + self.foot_radius                                         # :336-338
+        self.updateState(q, feedback=False)
+        jc = self.current_joint_config[:, 7:]
+        self.FL_leg, self.FR_leg, self.RL_leg, self.RR_leg, self.grip = jc[:, 0:3], jc[:, 3:6], jc[:, 6:9], jc[:, 9:12], jc[:, 12:]
+        self.dt = self.step_time
+        self.initialised = was_initialised
+        return self.current_joint_config
+
     # ---------------------------------------------------------------------------------- :354-383
     def _log_previous_states(self):
         mem = torch.empty_like(self._mem)
@@ -536,14 +604,14 @@ class RobotModel:
 
     # ---------------------------------------------------------------------------------- the fused tick :1330-1412
     def step(self, target_cartesian_pos_EE, target_cartesian_pos_trunk, imu_quat=None, advance=True,
-             plain_integrate=False):
+             plain_integrate=False, constraint_mask=None):
         """One fused launch: FK + Jacobians + task stack + bounds + constraints + QP (+ integrate / base estimate).
 
         Returns qdot [N, nv]; ``last_status`` / ``last_iters`` / ``last_active_set`` hold the per-state QP report.
         With ``advance`` the task memory and ``current_joint_config`` move on in place, as runWBC does.
         """
         T = self._pack_targets(target_cartesian_pos_EE, target_cartesian_pos_trunk)
-        cfg = self._config()
+        cfg = self._config(constraint_mask=constraint_mask)
         imu = self._as_batch(imu_quat, 4) if imu_quat is not None else None
         q_next = torch.empty_like(self.current_joint_config) if advance else None
         io = self._io(targets=T, qdot=self.qdot, status=self.last_status, iters=self.last_iters,

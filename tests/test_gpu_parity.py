@@ -289,3 +289,18 @@ def test_config3_extension_rows_full_size():
     same_set = (robot.last_active_set[:n].cpu().numpy().astype(np.uint64) == ref["active_set"]).all(axis=1)
     print("config3: identical pivoting path", same_path.mean(), "identical active set", same_set.mean())
     assert same_path.mean() > 0.97 and same_set.mean() > 0.90      # measured on B200: 0.992 / 0.950 (degenerate vertices)
+
+
+def test_bootstrap_matches_oracle():
+    """f4: the constructor bootstrap (setInitialState, Robot_Wrapper4.py:196-351) batched -- 60 of its 2000 ticks
+    (linear EE trajectories, bounds-only QP, plain integrate) and the final re-basing, against the oracle."""
+    import wbc_b200
+    from oracle.robot_wrapper4 import RobotModel as ORM
+    name, K = "a1_wx200", 60
+    robot = wbc_b200.RobotModel(name, batch=3, device="cuda:0")
+    qf = robot.setInitialState(bootstrap_steps=K).cpu().numpy()
+    orm = ORM(H.oracle_model(name), run_bootstrap=True, bootstrap_steps=K)     # the constructor runs it (:161), as the reference does
+    assert (robot.last_status == 0).all()
+    assert np.abs(qf - np.asarray(orm.current_joint_config)[None]).max() < 1e-8
+    assert np.abs(robot.FL_leg.cpu().numpy() - np.asarray(orm.FL_leg)[None]).max() < 1e-8
+    assert np.abs(robot.grip.cpu().numpy() - np.asarray(orm.grip)[None]).max() < 1e-8
