@@ -145,3 +145,22 @@ def test_product_package_never_imports_the_oracle():
     code = ("import sys; sys.path.insert(0, %r); import wbc_b200; "
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'" % ROOT)
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_mocap_ingestion_matches_the_fixture_rows(tmp_path):
+    """f4: playback files (tests_NOT_FOR_USE/mocap_wx200.txt) are FR, FL, RR, RL in file order; the golden rows are the same
+    frames already in Pinocchio order (tools/make_fixtures.py read them from the reference)."""
+    import json
+    import numpy as np
+    from wbc_b200 import mocap
+    rows = np.array(json.load(open(os.path.join(ROOT, "tests", "golden", "mocap_rows.json")))["wx200"])
+    bullet = mocap.pinocchio_to_bullet(rows)
+    path = tmp_path / "mocap.txt"
+    with open(path, "w") as fh:
+        for i, r in enumerate(bullet):
+            fh.write(f"{i + 1:12d}, {588975 + 2 * i:11d}, " + ", ".join(f"{v:11.6f}" for v in r) + "\n")
+    frames = mocap.load_mocap(str(path), n_joints=20)
+    assert frames.shape == rows.shape and np.abs(frames - rows).max() < 1e-9
+    assert np.abs(mocap.bullet_to_pinocchio(mocap.pinocchio_to_bullet(rows)) - rows).max() == 0.0
+    q = mocap.configurations(frames)
+    assert q.shape == (rows.shape[0], 27) and (q[:, 6] == 1.0).all()

@@ -304,3 +304,31 @@ def test_bootstrap_matches_oracle():
     assert np.abs(qf - np.asarray(orm.current_joint_config)[None]).max() < 1e-8
     assert np.abs(robot.FL_leg.cpu().numpy() - np.asarray(orm.FL_leg)[None]).max() < 1e-8
     assert np.abs(robot.grip.cpu().numpy() - np.asarray(orm.grip)[None]).max() < 1e-8
+
+
+def test_com_rows_match_oracle():
+    """f3: CoMConstraint (Robot_Wrapper4.py:669-694) = rows x, y of jacobianCenterOfMass with the box between the RR and
+    FL feet.  The reference's recorded CoM Jacobian (Jacobians.py:27-42) is stale against the current URDF masses, so
+    the pin is the oracle (whose CoM Jacobian is checked against the derivative of the CoM on the CPU).  Tilted bases
+    can make the box empty: both sides must then agree that the QP is infeasible."""
+    from oracle import c_port
+    name, N = "a1_wx200", 64
+    cons = dict(CoM=True, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+    robot = _robot(name, N, P1_TASKS, cons, True)
+    q, targets = _load(robot, N, 20260002, 5e-4)
+    mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+    asm = robot.assemble(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], want=("C", "Clb", "Cub"))
+    ref = H.oracle_step_batch(name, robot, q, targets.cpu().numpy(), mem0.cpu().numpy(), ref0.cpu().numpy(), solve=False)
+    assert asm["C"].shape[1] == 18
+    assert _maxabs(asm["C"].cpu().numpy() - ref["C"]) < FK_TOL
+    for k in ("Clb", "Cub"):
+        assert _maxabs(asm[k].cpu().numpy() - ref[k]) < 1e-9 * max(1.0, _maxabs(ref[k]))
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=False).cpu().numpy()
+    ts, table = c_port.table_struct(name)
+    cref = c_port.step(ts, c_port.config_struct(robot, table), q, targets.cpu().numpy(), mem0.cpu().numpy(),
+                       ref0.cpu().numpy(), robot.dt)
+    st = robot.last_status.cpu().numpy()
+    assert ((st & 2) == (cref["status"] & 2)).all()
+    ok = st == 0
+    assert ok.sum() >= N // 4
+    assert np.abs(x[ok] - cref["qdot"][ok]).max() < QP_TOL
