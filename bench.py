@@ -367,6 +367,19 @@ def run_ours(args):
         torch.cuda.synchronize()
         lat_us = float(np.median([a_.elapsed_time(b_) for a_, b_ in evl]) * 1e3)
 
+    # ---- the FK + frame-Jacobian accessor kernel (HBM-write bound, SURVEY 8d: 6 (12 + 6 nv) 8 + 8 nq bytes per state) ----
+    fkj = None
+    if rank == 0:
+        robot.frameJacobians(cabi.RF_LOCAL_WORLD_ALIGNED)
+        torch.cuda.synchronize()
+        ef = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a_, b_ in ef:
+            a_.record(); robot.frameJacobians(cabi.RF_LOCAL_WORLD_ALIGNED); b_.record()
+        torch.cuda.synchronize()
+        fkj_ms = float(np.median([a_.elapsed_time(b_) for a_, b_ in ef]))     # includes two output allocations (async)
+        fkj_bytes = (6 * (12 + 6 * table.nv) * 8 + 8 * table.nq) * n_local
+        fkj = {"ms": fkj_ms, "bytes_per_state": 6 * (12 + 6 * table.nv) * 8 + 8 * table.nq, "gbs": fkj_bytes / fkj_ms / 1e6}
+
     # ---- verification gather (off the timed path): NCCL all_gather of solutions / status -------------
     verified = status_ok and e2e_ok
     checksum = float(robot.qdot.double().abs().sum().item())
@@ -426,6 +439,9 @@ def run_ours(args):
                              "unit": "GB/s", "frac": bytes_state * n_local / kern_s / 1e9 / hbm_peak,
                              "bytes_per_state": bytes_state,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"},
+            "roofline_fk_jac": {"bound": "hbm", "kernel": "wbc_fk_jac_kernel (6 frames, LOCAL_WORLD_ALIGNED, placements + Jacobians)",
+                                "achieved": fkj["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": fkj["gbs"] / hbm_peak,
+                                "bytes_per_state": fkj["bytes_per_state"], "ms": fkj["ms"]},
             "mean_qp_iterations": kbar, "verified": verified, "checksum_abs_qdot": checksum,
             "launch": info, "wall_s_timed_region": wall,
         }

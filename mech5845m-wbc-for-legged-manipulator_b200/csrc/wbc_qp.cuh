@@ -19,11 +19,9 @@
 // LD is odd so that both row-wise (lane = row) and column-wise (lane = column) sweeps are free of
 // shared-memory bank conflicts beyond the 2-wavefront minimum of 64-bit accesses.
 //
-// Two bodies share the same algorithm and the same pivoting decisions:
-//   warp_qp_solve_ct<NV>  compile-time size: every inner loop is a jump into a fully unrolled
-//                         sequence (switch fall-through), so each element costs LDS + LDS + DFMA with
-//                         immediate offsets and two independent accumulators;
-//   warp_qp_solve_rt      run-time size (1 <= n <= 32) for the generic QP(A, b, ...) drop-in.
+// This file holds the run-time-size body (1 <= n <= 32, everything in shared memory) behind the generic
+// QP(A, b, ...) drop-in; the robot sizes (nv = 18 / 25 / 26) use the register-resident solver of
+// wbc_qp_reg.cuh, which follows the same algorithm and the same pivoting decisions.
 #pragma once
 #include "wbc_device.cuh"
 
@@ -80,324 +78,6 @@ __device__ __forceinline__ void pack_active_sets(int lane, int n, int nC, int bs
   const unsigned up_r = __ballot_sync(WBC_FULL_MASK, lane < nC && (cstat & 2));
   res.act_box = spread_bits(lo_b) | (spread_bits(up_b) << 1);
   res.act_rows = spread_bits(lo_r) | (spread_bits(up_r) << 1);
-}
-
-// =================================================================================================
-// compile-time size
-// =================================================================================================
-template <int NV>
-__device__ __forceinline__ QpResult warp_qp_solve_ct(const QpShared S, const int nC, const double g, const double lb,
-                                                     const double ub, const double clb, const double cub,
-                                                     const int max_iter, double& x_out) {
-  constexpr int n = NV;
-  constexpr int LD = NV | 1;
-  const int lane = threadIdx.x & 31;
-  const int li = lane < NV ? lane : NV - 1;      // row index clamped: idle lanes shadow the last row (reads only)
-  const bool act = lane < NV;
-  double* __restrict__ M0 = S.M0;
-  double* __restrict__ J = S.J;
-  const double* __restrict__ C = S.C;
-  double* __restrict__ vd = S.vd;
-  QpResult res;
-  res.status = 0;
-  res.iters = 0;
-
-  // ---- Cholesky H = L L^T in place (lower triangle), pivots clamped ---------------------------
-  double hd = act ? M0[li * LD + li] : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) hd = fmax(hd, __shfl_xor_sync(WBC_FULL_MASK, hd, o));
-  const double piv_min = WBC_QP_PIVOT_REL * fmax(hd, 0.0);
-  {
-    double* rowi = M0 + li * LD;
-#pragma unroll 1
-    for (int k = 0; k < n; ++k) {
-      const double* rowk = M0 + k * LD;
-      double s0 = rowi[k], s1 = 0.0;
-      switch (k) {
-#define WBC_CH(j) case (j + 1): if ((j) < NV) { if ((j) & 1) s1 = fma(-rowi[j], rowk[j], s1); else s0 = fma(-rowi[j], rowk[j], s0); }
-        WBC_REP32_DESC(WBC_CH)
-#undef WBC_CH
-        default: break;
-      }
-      const double s = s0 + s1;
-      double dk = __shfl_sync(WBC_FULL_MASK, s, k);
-      if (!(dk > piv_min)) {
-        dk = piv_min > 0.0 ? piv_min : 1.0;
-        res.status |= WBC_QP_NOT_PD;
-      }
-      const double r = rsqrt(dk);
-      if (lane == k) {
-        rowi[k] = dk * r;
-        vd[k] = r;                      // 1 / L_kk, used by the triangular inverse below
-      } else if (lane > k && act) {
-        rowi[k] = s * r;
-      }
-      __syncwarp();
-    }
-  }
-
-  // ---- J = L^-T : lane c computes column c of L^-1 and stores it as row c of J -----------------
-  {
-    double* rowc = J + li * LD;
-#pragma unroll 1
-    for (int i = 0; i < n; ++i) {
-      const double* Li = M0 + i * LD;
-      double a0 = (i == lane) ? 1.0 : 0.0, a1 = 0.0;
-      switch (i) {
-#define WBC_INV(j) case (j + 1): if ((j) < NV) { if ((j) & 1) a1 = fma(-Li[j], rowc[j], a1); else a0 = fma(-Li[j], rowc[j], a0); }
-        WBC_REP32_DESC(WBC_INV)
-#undef WBC_INV
-        default: break;
-      }
-      if (act) rowc[i] = (a0 + a1) * vd[i];
-    }
-  }
-  S.vg[lane] = act ? g : 0.0;
-  __syncwarp();
-
-  // ---- unconstrained minimiser x = -J J^T g  (J is upper triangular here; zeros elsewhere) -----
-  double x = 0.0;
-  {
-    double w0 = 0.0, w1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (i & 1) w1 = fma(J[i * LD + li], S.vg[i], w1);
-      else w0 = fma(J[i * LD + li], S.vg[i], w0);
-    }
-    __syncwarp();
-    vd[lane] = act ? (w0 + w1) : 0.0;
-    __syncwarp();
-    const double* rowi = J + li * LD;
-    double x0 = 0.0, x1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      if (j & 1) x1 = fma(-rowi[j], vd[j], x1);
-      else x0 = fma(-rowi[j], vd[j], x0);
-    }
-    x = act ? (x0 + x1) : 0.0;
-  }
-  __syncwarp();
-
-  // ---- working set ----------------------------------------------------------------------------------
-  int iq = 0, p_eq = 0;
-  int ws_c = -1, slot = lane;                // per working-set position (lane = position)
-  double u = 0.0, rinv = 0.0;
-  int bstat = 0, cstat = 0;                  // per box (lane = variable) / per row (lane = row): 0 none 1 lower 2 upper 3 eq
-
-  unsigned eq_mask_box = __ballot_sync(WBC_FULL_MASK, act && lb == ub);
-  unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && clb == cub);
-
-  bool done = false;
-#pragma unroll 1
-  while (!done) {
-    int ip, side;
-    bool is_eq = false;
-    // ------------------------------------------------------------ pick the entering constraint
-    if (eq_mask_box) {
-      ip = __ffs(eq_mask_box) - 1;
-      eq_mask_box &= eq_mask_box - 1;
-      side = -1; is_eq = true;
-    } else if (eq_mask_row) {
-      ip = n + __ffs(eq_mask_row) - 1;
-      eq_mask_row &= eq_mask_row - 1;
-      side = -1; is_eq = true;
-    } else {
-      S.vx[lane] = x;
-      __syncwarp();
-      double best = 0.0;
-      int bidx = 0x7fffffff;
-      int myside_b = -1, myside_c = -1;
-      if (act && bstat == 0) {
-        const double slo = x - lb, sup = ub - x;
-        best = fmin(slo, sup);
-        bidx = lane;
-        myside_b = (slo <= sup) ? -1 : +1;
-      }
-      {
-        const double* Cr = C + (lane < nC ? lane : 0) * LD;
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          if (j & 1) a1 = fma(Cr[j], S.vx[j], a1);
-          else a0 = fma(Cr[j], S.vx[j], a0);
-        }
-        if (lane < nC && cstat == 0) {
-          const double ax = a0 + a1;
-          const double slo = ax - clb, sup = cub - ax;
-          const double v = fmin(slo, sup);
-          myside_c = (slo <= sup) ? -1 : +1;
-          if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
-        }
-      }
-      if (bidx == 0x7fffffff) best = 0.0;
-      warp_argmin(best, bidx);
-      if (!(best < -WBC_QP_FEAS_TOL)) break;                       // primal feasible: optimal
-      ip = bidx;
-      const int src = (ip < n) ? ip : ip - n;
-      side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);
-    }
-    const double sgn = (side > 0) ? -1.0 : 1.0;                    // normal = sgn * a_ip
-    double u_new = 0.0;
-
-    // ------------------------------------------------------------ inner loop (GI step 2)
-#pragma unroll 1
-    while (true) {
-      if (!is_eq && res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; done = true; break; }
-      res.iters++;
-      // d = J^T n
-      double d;
-      if (ip < n) {
-        d = sgn * J[ip * LD + li];
-      } else {
-        const double* Cr = C + (ip - n) * LD;
-        double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          if (i & 1) d1 = fma(J[i * LD + li], Cr[i], d1);
-          else d0 = fma(J[i * LD + li], Cr[i], d0);
-        }
-        d = sgn * (d0 + d1);
-      }
-      if (!act) d = 0.0;
-      vd[lane] = d;
-      // dd = |d|^2, dd2 = |d2|^2 (columns >= iq)
-      double dd = d * d, dd2 = (lane >= iq) ? d * d : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dd += __shfl_xor_sync(WBC_FULL_MASK, dd, o);
-        dd2 += __shfl_xor_sync(WBC_FULL_MASK, dd2, o);
-      }
-      __syncwarp();
-      // z = J2 d2
-      double* rowi = J + li * LD;
-      double z0 = 0.0, z1 = 0.0;
-      switch (iq) {
-#define WBC_Z(j) case (j): if ((j) < NV) { if ((j) & 1) z1 = fma(rowi[j], vd[j], z1); else z0 = fma(rowi[j], vd[j], z0); }
-        WBC_REP32_ASC(WBC_Z)
-#undef WBC_Z
-        default: break;
-      }
-      const double z = z0 + z1;
-      // r = R^-1 d1 on the inequality block [p_eq, iq)
-      double rr = (lane < iq) ? d : 0.0;
-#pragma unroll 1
-      for (int k = iq - 1; k >= p_eq; --k) {
-        const int slot_k = __shfl_sync(WBC_FULL_MASK, slot, k);
-        const double rk = __shfl_sync(WBC_FULL_MASK, rr * rinv, k);
-        if (lane == k) rr = rk;
-        else if (lane < k && lane >= p_eq) rr -= M0[lane * LD + slot_k] * rk;
-      }
-      // constraint value at x:  s = n.x - bnd  (negative when violated)
-      double s_ip;
-      if (ip < n) {
-        const double xi = __shfl_sync(WBC_FULL_MASK, x, ip);
-        const double lo_i = __shfl_sync(WBC_FULL_MASK, lb, ip), up_i = __shfl_sync(WBC_FULL_MASK, ub, ip);
-        s_ip = (side > 0) ? (up_i - xi) : (xi - lo_i);
-      } else {
-        const double* Cr = C + (ip - n) * LD;
-        const double ax = warp_sum(act ? Cr[li] * x : 0.0);
-        const double lo_i = __shfl_sync(WBC_FULL_MASK, clb, ip - n), up_i = __shfl_sync(WBC_FULL_MASK, cub, ip - n);
-        s_ip = (side > 0) ? (up_i - ax) : (ax - lo_i);
-      }
-      const bool dependent = dd2 <= WBC_QP_DEP_TOL * dd;
-
-      if (is_eq) {
-        if (dependent) {                                             // redundant (or inconsistent) equality
-          if (fabs(s_ip) > 1e-8) res.status |= WBC_QP_INFEASIBLE;
-          break;
-        }
-        const double t = -s_ip / dd2;
-        x += t * z;
-        u_new = t;
-      } else {
-        // dual step length over active inequalities
-        double t1 = INFINITY;
-        int l = 0x7fffffff;
-        if (lane >= p_eq && lane < iq && rr > 0.0) { t1 = u / rr; l = lane; }
-        warp_argmin(t1, l);
-        const double t2 = dependent ? INFINITY : -s_ip / dd2;
-        const double t = fmin(t1, t2);
-        if (!(t < INFINITY)) { res.status |= WBC_QP_INFEASIBLE; done = true; break; }
-        if (lane >= p_eq && lane < iq) u -= t * rr;
-        u_new += t;
-        if (!dependent) x += t * z;
-        if (dependent || !(t2 <= t1)) {
-          // ---------------------------------------------------- drop working-set position l
-          const int c_drop = __shfl_sync(WBC_FULL_MASK, ws_c, l);
-#pragma unroll 1
-          for (int k = l; k < iq - 1; ++k) {
-            const int slot_k1 = __shfl_sync(WBC_FULL_MASK, slot, k + 1);
-            const double a = M0[k * LD + slot_k1], b = M0[(k + 1) * LD + slot_k1];
-            const double rho = sqrt(a * a + b * b);
-            const double cg = (rho > 0.0) ? a / rho : 1.0, sg = (rho > 0.0) ? b / rho : 0.0;
-            __syncwarp();                                             // everyone has read a, b before rows k, k+1 change
-            if (lane > k && lane < iq) {
-              const double r0 = M0[k * LD + slot], r1 = M0[(k + 1) * LD + slot];
-              M0[k * LD + slot] = cg * r0 + sg * r1;
-              M0[(k + 1) * LD + slot] = -sg * r0 + cg * r1;
-            }
-            if (act) {
-              const double j0 = rowi[k], j1 = rowi[k + 1];
-              rowi[k] = cg * j0 + sg * j1;
-              rowi[k + 1] = -sg * j0 + cg * j1;
-            }
-            __syncwarp();
-          }
-          {
-            const int dropped_slot = __shfl_sync(WBC_FULL_MASK, slot, l);
-            const int nc_ = __shfl_down_sync(WBC_FULL_MASK, ws_c, 1);
-            const int nslot = __shfl_down_sync(WBC_FULL_MASK, slot, 1);
-            const double nu = __shfl_down_sync(WBC_FULL_MASK, u, 1);
-            if (lane >= l && lane < iq - 1) { ws_c = nc_; slot = nslot; u = nu; }
-            if (lane == iq - 1) { slot = dropped_slot; ws_c = -1; u = 0.0; }
-            if (lane >= l && lane < iq - 1) rinv = 1.0 / M0[lane * LD + slot];
-            if (c_drop < n) { if (lane == c_drop) bstat = 0; }
-            else if (lane == c_drop - n) cstat = 0;
-            iq--;
-          }
-          __syncwarp();
-          continue;                                                   // retry the same candidate
-        }
-      }
-      // -------------------------------------------------------- full step: constraint ip enters at position iq
-      {
-        const double d_iq = __shfl_sync(WBC_FULL_MASK, d, iq);
-        const double nrm = sqrt(dd2);
-        const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
-        const double v_iq = d_iq + sigma;
-        const double beta = 1.0 / (sigma * v_iq);
-        const double jiq = rowi[iq];
-        if (lane == iq) vd[iq] = v_iq;
-        __syncwarp();
-        const double nbw = -beta * (z + sigma * jiq);
-        if (act) switch (iq) {
-#define WBC_HH(j) case (j): if ((j) < NV) { rowi[j] = fma(nbw, vd[j], rowi[j]); }
-          WBC_REP32_ASC(WBC_HH)
-#undef WBC_HH
-          default: break;
-        }
-        const int slot_new = __shfl_sync(WBC_FULL_MASK, slot, iq);
-        if (lane < iq) M0[lane * LD + slot_new] = d;
-        if (lane == iq) {
-          M0[iq * LD + slot_new] = -sigma;
-          rinv = -1.0 / sigma;
-          ws_c = ip;
-          u = u_new;
-        }
-        const int st = is_eq ? 3 : (side > 0 ? 2 : 1);
-        if (ip < n) { if (lane == ip) bstat = st; }
-        else if (lane == ip - n) cstat = st;
-        iq++;
-        if (is_eq) p_eq = iq;
-        __syncwarp();
-      }
-      break;
-    }
-  }
-
-  x_out = x;
-  pack_active_sets(lane, n, nC, bstat, cstat, res);
-  return res;
 }
 
 // =================================================================================================

@@ -332,3 +332,32 @@ def test_com_rows_match_oracle():
     ok = st == 0
     assert ok.sum() >= N // 4
     assert np.abs(x[ok] - cref["qdot"][ok]).max() < QP_TOL
+
+
+def test_ragged_and_empty_batches():
+    """Batch-size invariance: a state's answer does not depend on how many other states ride in the launch
+    (1, 13, one more than a full wave of 148 x 12 warps), and an empty batch is a no-op."""
+    import ctypes as C
+    import wbc_b200
+    from wbc_b200 import _cabi as cabi
+    name = "a1_wx200"
+    big_n = 148 * 12 + 1
+    big = _robot(name, big_n, P1_TASKS, P2_CONS, True)
+    q, targets = _load(big, big_n, 20260007, 5e-3)
+    mem0, ref0 = big._mem.clone(), big._ref.clone()
+    xb = big.step(targets[:, :15].reshape(big_n, 5, 3), targets[:, 15:18], advance=False).clone()
+    itb, actb = big.last_iters.clone(), big.last_active_set.clone()
+    assert (big.last_status == 0).all()
+    for n in (1, 13):
+        small = _robot(name, n, P1_TASKS, P2_CONS, True)
+        small.current_joint_config.copy_(big.current_joint_config[-n:])
+        small._mem.copy_(mem0[-n:]); small._ref.copy_(ref0[-n:])
+        xs = small.step(targets[-n:, :15].reshape(n, 5, 3), targets[-n:, 15:18], advance=False)
+        assert torch.equal(xs, xb[-n:])                       # bit-identical: same code path, same data
+        assert torch.equal(small.last_iters, itb[-n:]) and torch.equal(small.last_active_set, actb[-n:])
+    # N = 0 through the C ABI: accepted, nothing launched
+    io = big._io(targets=targets, qdot=big.qdot, status=big.last_status, iters=big.last_iters)
+    cfg = big._config()
+    assert cabi.load().wbc_step(big._model, C.byref(cfg), C.byref(io), 0, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(big.qdot, xb)
