@@ -77,43 +77,108 @@ struct FkJacParams {
   double* out_Jw;
 };
 
-__global__ void __launch_bounds__(256) wbc_fk_jac_kernel(const __grid_constant__ FkJacParams P) {
+#ifndef WBC_FKJ_CTAS
+#define WBC_FKJ_CTAS 2      // 128 registers: 16 warps per SM (3 CTAs spill, measured slower)
+#endif
+__global__ void __launch_bounds__(256, WBC_FKJ_CTAS) wbc_fk_jac_kernel(const __grid_constant__ FkJacParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
   stage_model(P.model, Ms);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
   const int per_warp = WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * per_warp;
-  double* oMi = ws;
-  double* oMf = ws + WBC_MAX_JOINTS * WBC_T_STRIDE;
-  double* qs = oMf + WBC_MAX_FRAMES * WBC_T_STRIDE;
+  const uint32_t M_a = smem_addr(Ms);
+  const uint32_t omi_a = smem_addr(ws);
+  const uint32_t omf_a = omi_a + 8 * WBC_MAX_JOINTS * WBC_T_STRIDE;      // placement of selected frame f at slot f
+  const uint32_t q_a = omf_a + 8 * WBC_MAX_FRAMES * WBC_T_STRIDE;
   const int nq = Ms->nq, nv = Ms->nv, nj = Ms->njoints;
+  // per selected frame (lane f < nsel): parent joint, support mask, offset -- loop invariant
+  int fpar = 0;
+  uint32_t fsupp_mine = 0;
+  double frR[9], frp[3];
+  bool fident = true;
+  if (lane < P.nsel) {
+    const int slot = P.slots[lane];
+    fpar = Ms->frame_parent[slot];
+    fsupp_mine = Ms->frame_supp[slot];
+    fident = Ms->fr_ident[slot] != 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) frR[i] = Ms->frR[slot][i];
+    frp[0] = Ms->frp[slot][0]; frp[1] = Ms->frp[slot][1]; frp[2] = Ms->frp[slot][2];
+  }
   for (long long s = (long long)blockIdx.x * wpc + warp; s < P.N; s += (long long)gridDim.x * wpc) {
-    for (int i = lane; i < nq; i += 32) qs[i] = P.q[s * nq + i];
+    for (int i = lane; i < nq; i += 32) sts_f64(q_a + 8 * i, P.q[s * nq + i]);
     __syncwarp();
-    warp_fk(Ms, qs, oMi, lane);
-    warp_frames(Ms, oMi, oMf, lane);
+    warp_fk_a(M_a, q_a, omi_a, lane);
     double Sc[6];
-    warp_jac_column(Ms, oMi, lane, Sc);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Sc[i] = 0.0;
+    if (lane < nv) {                                  // column `lane` of data.J (run-time nv: same code as warp_jac_col_a)
+      const uint32_t Ta = omi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(col_joint) + 4 * lane);
+      double R[9], axl[3], aw[3];
+      lds_mat3(Ta, R);
+      lds_vec3(M_a + WBC_MOFF(col_axis) + 24 * lane, axl);
+      mat3_vec(R, axl, aw);
+      if (lds_s32(M_a + WBC_MOFF(col_ang) + 4 * lane)) {
+        double p[3];
+        lds_vec3(Ta + 72, p);
+        cross3(p, aw, Sc);
+        Sc[3] = aw[0]; Sc[4] = aw[1]; Sc[5] = aw[2];
+      } else {
+        Sc[0] = aw[0]; Sc[1] = aw[1]; Sc[2] = aw[2];
+      }
+    }
+    if (lane < P.nsel) {                              // updateFramePlacements for the selected frames
+      double Rp[9], R[9], p[3], pp[3] = {0.0, 0.0, 0.0};
+      if (fpar == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rp[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      } else {
+        lds_mat3(omi_a + 8 * WBC_T_STRIDE * fpar, Rp);
+        lds_vec3(omi_a + 8 * (WBC_T_STRIDE * fpar + 9), pp);
+      }
+      if (fident) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = Rp[i];
+      } else {
+        mat3_mul(Rp, frR, R);
+      }
+      mat3_vec(Rp, frp, p);
+      const uint32_t oa = omf_a + 8 * WBC_T_STRIDE * lane;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) sts_f64(oa + 8 * i, R[i]);
+      sts_f64(oa + 72, p[0] + pp[0]); sts_f64(oa + 80, p[1] + pp[1]); sts_f64(oa + 88, p[2] + pp[2]);
+    }
+    __syncwarp();
     if (P.out_oMi) {
       for (int i = lane; i < nj * 12; i += 32) {
         const int j = i / 12, e = i % 12;
-        double v = oMi[j * WBC_T_STRIDE + e];
+        double v = lds_f64(omi_a + 8 * (j * WBC_T_STRIDE + e));
         if (j == 0) v = (e == 0 || e == 4 || e == 8) ? 1.0 : 0.0;
         P.out_oMi[s * nj * 12 + i] = v;
       }
     }
     if (P.out_Jw && lane < nv)
       for (int r = 0; r < 6; ++r) P.out_Jw[(s * 6 + r) * nv + lane] = Sc[r];
-    for (int f = 0; f < P.nsel; ++f) {
-      const int slot = P.slots[f];
-      const double* T = oMf + slot * WBC_T_STRIDE;
-      if (P.out_oMf && lane < 12) P.out_oMf[(s * P.nsel + f) * 12 + lane] = T[lane];
-      if (P.out_J && lane < nv) {
-        double Jc[6];
-        frame_jac_column(Sc, Ms->frame_supp[slot], lane, T, P.rf, Jc);
+    if (P.out_oMf)                                    // [N, nsel, 12]: contiguous per state
+      for (int i = lane; i < P.nsel * 12; i += 32)
+        P.out_oMf[s * P.nsel * 12 + i] = lds_f64(omf_a + 8 * ((i / 12) * WBC_T_STRIDE + (i % 12)));
+    if (P.out_J) {
+      double* Jout = P.out_J + s * (long long)P.nsel * 6 * nv + lane;
+      for (int f = 0; f < P.nsel; ++f) {
+        const uint32_t supp = __shfl_sync(WBC_FULL_MASK, fsupp_mine, f);
+        double T[12], Jc[6];
+        const uint32_t ta = omf_a + 8 * WBC_T_STRIDE * f;
+        if (P.rf == WBC_RF_LOCAL) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) P.out_J[((s * P.nsel + f) * 6 + r) * nv + lane] = Jc[r];
+          for (int i = 0; i < 9; ++i) T[i] = lds_f64(ta + 8 * i);
+        }
+        T[9] = lds_f64(ta + 72); T[10] = lds_f64(ta + 80); T[11] = lds_f64(ta + 88);
+        frame_jac_column(Sc, supp, lane, T, P.rf, Jc);
+        if (lane < nv) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r) Jout[(f * 6 + r) * nv] = Jc[r];
+        }
       }
     }
     __syncwarp();
@@ -557,7 +622,7 @@ static int fk_common(const WbcModel* model, FkJacParams& P, void* stream) {
   CUDA_TRY(cudaFuncSetAttribute(wbc_fk_jac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (P.N == 0) return WBC_OK;
   long long need = (P.N + wpc - 1) / wpc;
-  const long long cap = (long long)model->sm_count * 4;
+  const long long cap = (long long)model->sm_count * WBC_FKJ_CTAS;
   const int grid = (int)(need < cap ? need : cap);
   wbc_fk_jac_kernel<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(P);
   CUDA_TRY(cudaGetLastError());
