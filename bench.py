@@ -265,6 +265,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -456,7 +460,8 @@ def run_ours(args):
             ts, table_c = c_port.table_struct(args.robot)
             chk = c_port.step(ts, c_port.config_struct(_p3_oracle(args.robot, args.dt), table_c), *arrays, args.dt, nthreads=1)
             line["max_abs_diff_vs_cpu_oracle"] = float(np.abs(chk["qdot"] - robot.qdot[:n_cpu].cpu().numpy()).max())
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
