@@ -303,21 +303,40 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        evs[k][0].record()
-        one_step()
-        evs[k][1].record()
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    per_step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = evs[0][0].elapsed_time(evs[-1][1])
-    clocks = sampler.stop() if rank == 0 else None
+    def timed_region():
+        """K steps between barriers, CUDA events on the launching stream; nvidia-smi clocks sampled while it runs
+        (the sampler keeps the GPU under the same load for >= 0.5 s so that a 100 ms poll sees it)."""
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            t_load = time.perf_counter()
+            while time.perf_counter() - t_load < 0.5:          # untimed: same kernel, lets the clock samples land under load
+                one_step()
+                torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t_wall0 = time.perf_counter()
+        for k in range(args.steps):
+            evs[k][0].record()
+            one_step()
+            evs[k][1].record()
+        barrier()
+        wall_ = time.perf_counter() - t_wall0
+        clocks_ = sampler.stop() if rank == 0 else None
+        return [a.elapsed_time(b) for a, b in evs], evs[0][0].elapsed_time(evs[-1][1]), wall_, clocks_
+
+    per_step_ms, total_ms, wall, clocks = timed_region()
+    remeasured = False
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    flag = torch.tensor([1.0 if (rank == 0 and clocks and bad & set(clocks.get("reasons", []))) else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if flag.item() > 0:                                        # throttled: cool down and measure once more
+        time.sleep(5.0)
+        per_step_ms, total_ms, wall, clocks = timed_region()
+        remeasured = True
+    if rank == 0 and clocks is not None:
+        clocks["remeasured"] = remeasured
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
