@@ -403,6 +403,32 @@ def run_ours(args):
         fkj_bytes = (6 * (12 + 6 * table.nv) * 8 + 8 * table.nq) * n_local
         fkj = {"ms": fkj_ms, "bytes_per_state": 6 * (12 + 6 * table.nv) * 8 + 8 * table.nq, "gbs": fkj_bytes / fkj_ms / 1e6}
 
+    # ---- BASELINE config 5 (optional): closed-loop horizon, K ticks, state resident on the device -----------------
+    rollout_line = None
+    if args.rollout > 0:
+        K = args.rollout
+        rr = wbc_b200.RobotModel(args.robot, batch=n_local, device=dev, dt=args.dt)
+        rr.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
+        rr.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+        rr.current_joint_config = robot.current_joint_config.clone(); rr._mem.copy_(mem0); rr._ref.copy_(robot._ref)
+        # feet stay planted (their rows are equalities); the gripper and trunk targets wander: per-robot random walk
+        gen = torch.Generator(device=dev); gen.manual_seed(args.seed + 5)
+        drift = torch.zeros(K, n_local, 18, dtype=torch.float64, device=dev)
+        drift[:, :, 12:18] = torch.randn(K, n_local, 6, dtype=torch.float64, device=dev, generator=gen).mul_(1e-4).cumsum(0)
+        traj = targets[None] + drift
+        ee_tr, tr_tr = traj[:, :, :15].reshape(K, n_local, 5, 3), traj[:, :, 15:18]
+        rr.rollout(ee_tr[:2], tr_tr[:2])                                   # warm-up
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(); rr.rollout(ee_tr, tr_tr); r1.record()
+        barrier()
+        tr_ms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr_ms, op=dist.ReduceOp.MAX)
+        rollout_line = {"ticks": K, "robots": n_global, "steps_per_s": n_global * K / (float(tr_ms.item()) * 1e-3),
+                        "ms_per_tick": float(tr_ms.item()) / K, "solved_fraction_last_tick": float((rr.last_status == 0).double().mean().item()),
+                        "mean_qp_iterations_last_tick": float(rr.last_iters.double().mean().item())}
+
     # ---- verification gather (off the timed path): NCCL all_gather of solutions / status -------------
     verified = status_ok and e2e_ok
     checksum = float(robot.qdot.double().abs().sum().item())
@@ -465,6 +491,7 @@ def run_ours(args):
             "roofline_fk_jac": {"bound": "hbm", "kernel": "wbc_fk_jac_kernel (6 frames, LOCAL_WORLD_ALIGNED, placements + Jacobians)",
                                 "achieved": fkj["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": fkj["gbs"] / hbm_peak,
                                 "bytes_per_state": fkj["bytes_per_state"], "ms": fkj["ms"]},
+            "rollout": rollout_line,
             "mean_qp_iterations": kbar, "verified": verified, "checksum_abs_qdot": checksum,
             "launch": info, "wall_s_timed_region": wall,
         }
@@ -499,6 +526,7 @@ def main():
     ap.add_argument("--dt", type=float, default=0.002)
     ap.add_argument("--seed", type=int, default=20260003)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout", type=int, default=0, help="BASELINE config 5: closed-loop horizon of K ticks (extra line on stderr)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -230,6 +230,14 @@ int wbc_qp_solve(int64_t N, int32_t nv, int32_t m, int32_t nC, const double* A, 
 /* the fused tick */
 int wbc_step(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, int64_t N, void* stream);
 
+/* Closed loop: K consecutive ticks (the tick loop of sim3.py:287-327 around runWBC, Robot_Wrapper4.py:1330-1412) for
+ * N robots, one fused launch per tick, configuration and task memory advanced in place on the device.
+ * io->q is read and overwritten (io->q_next must be NULL or equal to io->q), io->mem_in likewise (io->mem_out NULL or
+ * equal); io->targets is ignored: tick k reads targets_traj[k] ([K, N, 18]).  imu_traj [K, N, 4] or NULL (base
+ * orientation fed back after each tick).  qdot / status / iters / active_set hold the last tick. */
+int wbc_rollout(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const double* targets_traj,
+                const double* imu_traj, int32_t K, int64_t N, void* stream);
+
 /* launch geometry the step kernel uses on the current device (for bench reporting) */
 int wbc_step_launch_info(const WbcModel* model, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* regs);
 

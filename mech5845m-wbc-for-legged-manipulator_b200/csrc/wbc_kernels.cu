@@ -699,6 +699,28 @@ int wbc_step(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, i
   return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
 }
 
+int wbc_rollout(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const double* targets_traj,
+                const double* imu_traj, int32_t K, int64_t N, void* stream) {
+  if (!io || !targets_traj || K < 0) return fail(WBC_ERR_INVALID_ARG, "null io / targets_traj or negative K%s");
+  if ((io->q_next && io->q_next != io->q) || (io->mem_out && io->mem_out != io->mem_in))
+    return fail(WBC_ERR_INVALID_ARG, "wbc_rollout advances q and mem in place%s");
+  WbcStepIO tick = *io;
+  tick.q_next = const_cast<double*>(io->q);
+  tick.mem_out = const_cast<double*>(io->mem_in);
+  StepParams P;
+  for (int k = 0; k < K; ++k) {
+    tick.targets = targets_traj + (size_t)k * N * WBC_TARGETS_STRIDE;
+    tick.imu_quat = imu_traj ? imu_traj + (size_t)k * N * 4 : nullptr;
+    int rc = check_cfg(model, cfg, &tick, &P);
+    if (rc != WBC_OK) return rc;
+    if (N < 0 || !tick.qdot || !tick.status || !tick.iters) return fail(WBC_ERR_INVALID_ARG, "qdot / status / iters are required%s");
+    P.N = N;
+    rc = launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
+    if (rc != WBC_OK) return rc;
+  }
+  return WBC_OK;
+}
+
 int wbc_step_launch_info(const WbcModel* model, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* regs) {
   if (!model) return fail(WBC_ERR_INVALID_ARG, "null model%s");
   StepParams P;

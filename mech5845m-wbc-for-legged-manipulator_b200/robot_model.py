@@ -699,16 +699,27 @@ class RobotModel:
         ``record`` the tuple (q history [K, N, nq], qdot history [K, N, nv], status history [K, N]).
         """
         K = int(target_EE_traj.shape[0])
+        if not record:
+            # one C-ABI call: K launches back to back, q and task memory advanced in place on the device
+            traj = torch.cat((target_EE_traj.to(self.device, torch.float64).reshape(K, self.N, 15),
+                              target_trunk_traj.to(self.device, torch.float64).reshape(K, self.N, 3)), dim=2).contiguous()
+            imu = imu_quat_traj.to(self.device, torch.float64).reshape(K, self.N, 4).contiguous() if imu_quat_traj is not None else None
+            self.current_joint_config = self.current_joint_config.contiguous().clone()
+            io = self._io(targets=traj, qdot=self.qdot, status=self.last_status, iters=self.last_iters,
+                          active_set=self.last_active_set)
+            with torch.cuda.device(self.device):
+                cabi.check(self._lib.wbc_rollout(self._model, C.byref(self._config()), C.byref(io), _ptr(traj), _ptr(imu), K,
+                                                 self.N, _stream_ptr()))
+            self._targets.copy_(traj[-1])
+            self.firstQP = False
+            return self.qdot
         qs, vs, st = [], [], []
         for k in range(K):
             imu = imu_quat_traj[k] if imu_quat_traj is not None else None
             self.step(target_EE_traj[k], target_trunk_traj[k], imu_quat=imu, advance=True)
-            if record:
-                qs.append(self.current_joint_config.clone()); vs.append(self.qdot.clone()); st.append(self.last_status.clone())
+            qs.append(self.current_joint_config.clone()); vs.append(self.qdot.clone()); st.append(self.last_status.clone())
         self.firstQP = False
-        if record:
-            return torch.stack(qs), torch.stack(vs), torch.stack(st)
-        return self.qdot
+        return torch.stack(qs), torch.stack(vs), torch.stack(st)
 
     def launch_info(self):
         g, b, s, r = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()

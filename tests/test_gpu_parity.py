@@ -239,6 +239,12 @@ def test_closed_loop_rollout_matches_oracle():
     mem0, ref0 = robot._mem.clone().cpu().numpy(), robot._ref.clone().cpu().numpy()
     qh, vh, sh = robot.rollout(traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18], record=True)
     assert (sh == 0).all()
+    # the single-call C-ABI rollout (wbc_rollout: K launches, state advanced in place) lands on the same state
+    twin = _robot(name, N, P1_TASKS, P2_CONS, True)
+    twin.current_joint_config = torch.as_tensor(q, device="cuda:0").clone()
+    twin._mem.copy_(torch.as_tensor(mem0, device="cuda:0")); twin._ref.copy_(torch.as_tensor(ref0, device="cuda:0"))
+    v_last = twin.rollout(traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18])
+    assert torch.equal(twin.current_joint_config, qh[-1]) and torch.equal(v_last, vh[-1]) and torch.equal(twin._mem, robot._mem)
     qh, vh = qh.cpu().numpy(), vh.cpu().numpy()
     rm = H.make_oracle(name, like=robot, dt=robot.dt)
     traj_h = traj.cpu().numpy()
