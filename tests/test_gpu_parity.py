@@ -160,6 +160,7 @@ def test_qp_kat_and_random_problems():
     A[:, 36:, :] = np.eye(n)[None] * (0.05 / 26)
     b = rng.normal(size=(N, m)) * 3
     lb = -rng.uniform(0, 2, (N, n)); ub = rng.uniform(0, 2, (N, n)); lb[:, 23:] = 0; ub[:, 23:] = 0
+    lb[::2, 5] = ub[::2, 5] = 0.3; lb[::3, 17] = ub[::3, 17] = -0.2     # variables fixed at non-zero values (eliminated up front)
     Cm = rng.normal(size=(N, nC, n)); Clb = -rng.uniform(0, 1, (N, nC)); Cub = rng.uniform(0, 1, (N, nC))
     Clb[:, 4:] = 0; Cub[:, 4:] = 0
     qp = wbc_b200.QP(A, b, lb, ub, np.transpose(Cm, (0, 2, 1)), Clb, Cub, n_of_velocity_dimensions=n)
