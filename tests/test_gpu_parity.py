@@ -368,3 +368,57 @@ def test_ragged_and_empty_batches():
     assert cabi.load().wbc_step(big._model, C.byref(cfg), C.byref(io), 0, None) == 0
     torch.cuda.synchronize()
     assert torch.equal(big.qdot, xb)
+
+
+def test_general_placements_and_axes(tmp_path):
+    """The A1 URDFs only have pure-translation placements and unit axes, which take exact shortcuts in the kernels.
+    A perturbed copy of the tree (rotated joint placements and frame offsets, a skew revolute axis, as in
+    laikago_vx300.urdf) drives the general code paths; FK, Jacobians and one full tick against the oracle."""
+    import json
+    import wbc_b200
+    from scipy.spatial.transform import Rotation as R
+    d = json.load(open(H.table_path("a1_wx200")))
+    rng = np.random.default_rng(12)
+    for j in (3, 6, 9, 15, 17):                                   # thighs and two arm joints: rotated placements
+        d["joints"][j]["R"] = R.from_euler("xyz", rng.uniform(-0.4, 0.4, 3)).as_matrix().reshape(-1).tolist()
+    ax = np.array([0.3, -0.5, 0.8]); ax /= np.linalg.norm(ax)
+    d["joints"][16]["axis"] = ax.tolist()                          # elbow about a skew axis
+    for f in d["frames"]:
+        if f["name"] in ("FR_foot_fixed", "gripper_bar", "imu_joint"):
+            f["R"] = R.from_euler("xyz", rng.uniform(-0.5, 0.5, 3)).as_matrix().reshape(-1).tolist()
+    path = tmp_path / "a1_wx200_general.json"
+    json.dump(d, open(path, "w"))
+    N = 64
+    robot = wbc_b200.RobotModel(str(path), batch=N, device="cuda:0")
+    robot.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
+    robot.setConstraints(**P2_CONS)
+    model = H.opin.Model.from_json(str(path))
+    data = model.createData()
+    q, targets = _load(robot, N, 31, 5e-4)
+    got = {rf: robot.frameJacobians(rf) for rf in (0, 1, 2)}
+    frames = robot.end_effector_index_list_frame + [robot.trunk_frame_index]
+    worst = 0.0
+    for s in range(0, N, 5):
+        H.opin.forwardKinematics(model, data, q[s])
+        H.opin.computeJointJacobians(model, data, q[s])
+        H.opin.updateFramePlacements(model, data)
+        for rf in (0, 1, 2):
+            oMf, J = got[rf]
+            for k, fid in enumerate(frames):
+                worst = max(worst, np.abs(J[s, k].cpu().numpy() - H.opin.getFrameJacobian(model, data, fid, rf)).max())
+                ref = np.concatenate([data.oMf[fid].rotation.reshape(-1), data.oMf[fid].translation])
+                worst = max(worst, np.abs(oMf[s, k].cpu().numpy() - ref).max())
+    assert worst < FK_TOL, worst
+    # one fused tick on the general tree
+    from oracle.robot_wrapper4 import RobotModel as ORM
+    mem0, ref0 = robot._mem.clone().cpu().numpy(), robot._ref.clone().cpu().numpy()
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=False).cpu().numpy()
+    rm = ORM(model, dt=robot.dt)
+    H.copy_settings(robot, rm)
+    tg = targets.cpu().numpy()
+    for s in range(0, N, 7):
+        r = H.oracle_step_one(rm, q[s], tg[s], mem0[s], ref0[s], solve=True, tail=False)
+        assert int(robot.last_status[s]) == int(r["status"])
+        if r["status"] == 0:
+            assert np.abs(x[s] - r["qdot"]).max() < QP_TOL
+            assert int(robot.last_iters[s]) == r["iters"]
