@@ -545,8 +545,7 @@ static int launch_step(const WbcModel* model, const StepParams& P, cudaStream_t 
   switch (model->host.nv) {
     case 25: return launch_step_t<25, DBG>(model, P, st, info);
     case 26: return launch_step_t<26, DBG>(model, P, st, info);
-    case 18: return launch_step_t<18, DBG>(model, P, st, info);
-    default: return fail(WBC_ERR_UNSUPPORTED, "step kernel is instantiated for nv in {18, 25, 26}%s");
+    default: return fail(WBC_ERR_UNSUPPORTED, "the fused step kernel is instantiated for nv = 25 (A1 + PX100) and nv = 26 (A1 + WX200)%s");
   }
 }
 
@@ -760,7 +759,6 @@ int wbc_qp_solve(int64_t N, int32_t nv, int32_t m, int32_t nC, const double* A, 
   // the robot sizes get the register-resident solver; any other 1 <= nv <= 32 the run-time-size one
   if (nv == 26) return launch_qp_reg<26>(P, sms, (cudaStream_t)stream);
   if (nv == 25) return launch_qp_reg<25>(P, sms, (cudaStream_t)stream);
-  if (nv == 18) return launch_qp_reg<18>(P, sms, (cudaStream_t)stream);
   const int LD = nv | 1;
   const int per_warp = 2 * nv * LD + nC * LD + 96 + ((2 * nv * LD + nC * LD) & 1);
   const int wpc = 8;

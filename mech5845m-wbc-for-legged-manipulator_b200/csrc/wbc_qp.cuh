@@ -20,7 +20,7 @@
 // shared-memory bank conflicts beyond the 2-wavefront minimum of 64-bit accesses.
 //
 // This file holds the run-time-size body (1 <= n <= 32, everything in shared memory) behind the generic
-// QP(A, b, ...) drop-in; the robot sizes (nv = 18 / 25 / 26) use the register-resident solver of
+// QP(A, b, ...) drop-in; the robot sizes (nv = 25 / 26) use the register-resident solver of
 // wbc_qp_reg.cuh, which follows the same algorithm and the same pivoting decisions.
 #pragma once
 #include "wbc_device.cuh"
