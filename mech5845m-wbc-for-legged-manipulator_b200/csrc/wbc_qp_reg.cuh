@@ -275,20 +275,107 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   int bstat = fixed ? 3 : 0, cstat = 0;      // 0 none 1 lower 2 upper 3 eq
   unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && lds_f64(S.clb + 8 * lane) == lds_f64(S.cub + 8 * lane));
 
+  // ---- equality rows first, in index order: no step-length logic, no multipliers, no column of R, no d1 ----
+#pragma unroll 1
+  while (eq_mask_row) {
+    const int c = __ffs(eq_mask_row) - 1;
+    eq_mask_row &= eq_mask_row - 1;
+    res.iters++;
+    if (crow == c) publish_row<ND>(vd_a + doff, Dr);                 // SPLIT: both halves write their segment
+    __syncwarp();
+    if (lane < iq) sts_f64(vd_a + 8 * lane, 0.0);
+    __syncwarp();
+    double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const double2 d2 = lds_f64x2(vd_a + 16 * p);
+      z0 = fma(Jr[2 * p], d2.x, z0);
+      e0 = fma(d2.x, d2.x, e0);
+      if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+      if (2 * p + 1 < NV) {
+        z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
+        e1 = fma(d2.y, d2.y, e1);
+        if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+      }
+    }
+    if (SPLIT) {
+#pragma unroll
+      for (int p = 0; p < ND / 2; ++p) {
+        const double2 d2 = lds_f64x2(vd_a + doff + 16 * p);
+        w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+        w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+      }
+    }
+    double w = w0 + w1;
+    if (SPLIT) w += __shfl_xor_sync(WBC_FULL_MASK, w, 16);
+    const double z = z0 + z1, dd2 = e0 + e1;
+    const double s_c = __shfl_sync(WBC_FULL_MASK, ax, c) - lds_f64(S.clb + 8 * c);     // C_c x - bound
+    if (dd2 <= WBC_QP_DEP_TOL * lds_f64(S.dd + 8 * (32 + c))) {      // redundant (or inconsistent) equality
+      if (fabs(s_c) > 1e-8) res.status |= WBC_QP_INFEASIBLE;
+      __syncwarp();
+      continue;
+    }
+    const double rs = fast_rsqrt(dd2);
+    const double t = -s_c * (rs * rs);
+    x = fma(t, z, x);
+    ax = fma(t, w, ax);
+    const double d_iq = lds_f64(vd_a + 8 * iq);
+    const double nrm = dd2 * rs;
+    const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
+    const double isig = (d_iq >= 0.0) ? rs : -rs;
+    const double v_iq = d_iq + sigma;
+    const double beta = isig * fast_rcp(v_iq);
+    double jiq = 0.0, diq = 0.0;
+    switch (iq) {
+#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; \
+        if (!SPLIT) diq = Dr[WBC_DX(j)]; \
+        else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
+        else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
+      WBC_REP32_ASC(WBC_PK)
+#undef WBC_PK
+      default: break;
+    }
+    if (SPLIT) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
+    const double nbJ = -beta * fma(sigma, jiq, z);
+    const double nbD = -beta * fma(sigma, diq, w);
+    if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const double2 v2 = lds_f64x2(vd_a + 16 * p);
+      Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
+      if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+      if (2 * p + 1 < NV) {
+        Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
+        if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
+      }
+    }
+    if (SPLIT) {
+#pragma unroll
+      for (int p = 0; p < ND / 2; ++p) {
+        const double2 v2 = lds_f64x2(vd_a + doff + 16 * p);
+        Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+        Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
+      }
+    }
+    if (lane == iq) { rinv = -isig; ws_c = n + c; u = t; }
+    if (lane == c) cstat = 3;
+    iq++;
+    p_eq = iq;
+    __syncwarp();
+  }
+
   // One flat loop: every pass is one step of the method for the current candidate (pick one if there is none).
-  bool have = false, is_eq = false, is_box = false;
+  // (inequalities only: the equalities are in the working set by now, so is_eq is a compile-time false here)
+  constexpr bool is_eq = false;
+  bool have = false, is_box = false;
   int ip = 0, side = -1, owner = 0;
   double sgn = 1.0, dd = 0.0, u_new = 0.0;
 #pragma unroll 1
   for (;;) {
     if (!have) {
       // ------------------------------------------------------------ pick the entering constraint
-      if (eq_mask_row) {
-        ip = n + __ffs(eq_mask_row) - 1;
-        eq_mask_row &= eq_mask_row - 1;
-        side = -1; is_eq = true;
-      } else {
-        is_eq = false;
+      {
         double best = 0.0;
         int bidx = 0x7fffffff;
         int myside_b = -1, myside_c = -1;
@@ -318,7 +405,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       u_new = 0.0;
       have = true;
     }
-    if (!is_eq && res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; break; }
+    if (res.iters >= max_iter) { res.status |= WBC_QP_MAXITER; break; }
     res.iters++;
     // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
     if (is_box) {
