@@ -78,7 +78,8 @@ __device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
     sts_f64x2(a0 + 16 * p, a[2 * p], (2 * p + 1 < N) ? a[(2 * p + 1 < N) ? 2 * p + 1 : 0] : 0.0);
 }
 
-template <int NV, bool SPLIT>
+// SYNC: the caller's warps run in lockstep groups (fused kernel): re-align between the straight-line phases
+template <int NV, bool SPLIT, bool SYNC = false>
 __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
                                                       const int nC, double g, const double lb_in, const double ub_in,
                                                       const int max_iter, double& x_out) {
@@ -152,6 +153,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     }
   }
 
+  if (SYNC) phase_sync<true>();
   // ---- phase B: forward substitutions L^-1 [I | g | C^T], column-oriented, all right-hand sides at once:
   //      lane i < NV: e_i (-> row i of J = L^-T), lane NV: g, second array: the rows of C with the fixed
   //      variables' coefficients moved into `shift`
@@ -224,6 +226,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     }
   }
 
+  if (SYNC) phase_sync<true>();
   // ---- |d|^2 of every constraint (invariant under the orthogonal updates), x0 = -J (L^-1 g), C x0 -----
   const uint32_t lo_a = rk_a, up_a = rk_a + 8 * 32;     // 1 / L_kk is dead now
   double x, ax;

@@ -422,27 +422,9 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
   }
 }
 
-// Phase barrier: the warps of a group re-align (named barrier per group of WBC_SYNC_GROUP warps; 0 = whole CTA).
-#ifndef WBC_SYNC_GROUP
-#define WBC_SYNC_GROUP 6       // two groups of six warps: 3.4 % faster than one group of 12 (less waiting for the slowest QP); three groups thrash the I-cache (-21 %)
+#ifndef WBC_QP_MID_SYNC
+#define WBC_QP_MID_SYNC 0
 #endif
-template <bool ON>
-__device__ __forceinline__ void phase_sync() {
-  if (ON) {
-#if WBC_SYNC_GROUP > 0
-    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int g = wid / WBC_SYNC_GROUP;
-    const int first = g * WBC_SYNC_GROUP;
-    const int cnt = (nw - first < WBC_SYNC_GROUP ? nw - first : WBC_SYNC_GROUP) * 32;
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(cnt) : "memory");
-#else
-    __syncthreads();
-#endif
-  } else {
-    __syncwarp();
-  }
-}
-
 #ifndef WBC_PHASE_SYNC
 #define WBC_PHASE_SYNC 1
 #endif
@@ -889,7 +871,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       QpRegShared S;
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
       S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
-      res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
+      res = warp_qp_solve_reg<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0)>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
     }
 
     phase_sync<PS>();            // (measured: dropping this barrier costs 6 %)
