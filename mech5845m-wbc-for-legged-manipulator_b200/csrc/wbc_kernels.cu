@@ -53,7 +53,7 @@ template <bool SPLIT> struct StepWarps {
   static constexpr int ctas = SPLIT ? WBC_STEP_CTAS : 1;
 };
 
-template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD>
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF>
 __global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>::ctas) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>
   const StepLayout L = step_layout(NV, P.nC);
   const int warp = threadIdx.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
-  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD>(P, Ms, ws, L);
+  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF>(P, Ms, ws, L);
 }
 
 // FK + frame Jacobians accessor (HBM-write bound): one state per warp
@@ -501,7 +501,7 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
 
 static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15); }
 
-template <int NV, bool DBG, bool SPLIT, bool FD>
+template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0>
 static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
   const StepLayout L = step_layout(NV, P.nC);
   const size_t per_warp = (size_t)L.total * sizeof(double);
@@ -512,7 +512,7 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
   if (warps > StepWarps<SPLIT>::value) warps = StepWarps<SPLIT>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
   const size_t smem = model_smem_bytes() + warps * per_warp;
-  auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD>;
+  auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD, NF>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + warps - 1) / warps;
   int grid = (int)(need < (long long)model->sm_count * ctas ? need : (long long)model->sm_count * ctas);
@@ -535,8 +535,13 @@ static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_
   const bool fd = (P.cfg.task_mask & WBC_TASK_JOINT) && (P.cfg.joint_mode == WBC_JOINT_MANI || P.cfg.joint_mode == WBC_JOINT_HYBRID);
   if (DBG)                                                                     // the accessor never reaches the solver
     return fd ? launch_step_k<NV, DBG, true, true>(model, P, st, info) : launch_step_k<NV, DBG, true, false>(model, P, st, info);
-  if (P.nC <= 16)
+  if (P.nC <= 16) {
+    // velDamperJointConstraints locks v >= gripper_joint_id - 2 + 6 (lb = ub = 0, :627-631): when these are exactly the
+    // last three DoFs (both arms) the solver eliminates them at compile time
+    if (NV - (P.cfg.gripper_joint_id - 2 + 6) == 3)
+      return fd ? launch_step_k<NV, DBG, true, true, 3>(model, P, st, info) : launch_step_k<NV, DBG, true, false, 3>(model, P, st, info);
     return fd ? launch_step_k<NV, DBG, true, true>(model, P, st, info) : launch_step_k<NV, DBG, true, false>(model, P, st, info);
+  }
   return fd ? launch_step_k<NV, DBG, false, true>(model, P, st, info) : launch_step_k<NV, DBG, false, false>(model, P, st, info);
 }
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return y;
 }
 
-#define WBC_IX(j) ((j) < NV ? (j) : 0)
+#define WBC_IX(j) ((j) < NQ ? (j) : 0)
 #define WBC_DX(j) (((j) >= 0 && (j) < ND) ? (j) : 0)
 
 // the calling lane publishes N register values as a[0..N) at shared address `a0` (zero padded to an even count)
@@ -78,21 +78,32 @@ __device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
     sts_f64x2(a0 + 16 * p, a[2 * p], (2 * p + 1 < N) ? a[(2 * p + 1 < N) ? 2 * p + 1 : 0] : 0.0);
 }
 
-// SYNC: the caller's warps run in lockstep groups (fused kernel): re-align between the straight-line phases
-template <int NV, bool SPLIT, bool SYNC = false>
+// SYNC: the caller's warps run in lockstep groups (fused kernel): re-align between the straight-line phases.
+// NF:   the last NF variables are known at compile time to be fixed (lb == ub, e.g. the locked gripper DoFs of
+//       velDamperJointConstraints, Robot_Wrapper4.py:627-631): they never enter the factorisation, the solver runs
+//       on NQ = NV - NF variables.  Contract: h[k] = H[lane][k] for lane < NQ and 0 for lane >= NQ; lb_in == ub_in
+//       on lanes [NQ, NV).  They are reported like the run-time fixed variables (equality-active, one working-set
+//       change each).
+#ifndef WBC_QP_KEQ
+#define WBC_QP_KEQ 12      // equality rows with a dedicated straight-line block each (static position in the working set)
+#endif
+template <int NV, bool SPLIT, bool SYNC = false, int NF = 0>
 __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
                                                       const int nC, double g, const double lb_in, const double ub_in,
                                                       const int max_iter, double& x_out) {
-  constexpr int n = NV;
-  constexpr int LD = NV | 1;
-  constexpr int LC = (NV + 1) & ~1;          // column stride of the stored L (even: 128-bit broadcast loads)
-  constexpr int NP = (NV + 1) / 2;           // pairs per vector
-  constexpr int HALF = SPLIT ? ((((NV + 1) / 2) + 1) & ~1) : NV;   // elements of a row's d vector per lane
+  constexpr int NQ = NV - NF;                // variables of the factorisation
+  constexpr int n = NQ;
+  constexpr int LD = NV | 1;                 // leading dimension of C (caller's layout) and of R
+  constexpr int LC = (NQ + 1) & ~1;          // column stride of the stored L (even: 128-bit broadcast loads)
+  constexpr int NP = (NQ + 1) / 2;           // pairs per vector
+  constexpr int HALF = SPLIT ? ((((NQ + 1) / 2) + 1) & ~1) : NQ;   // elements of a row's d vector per lane
   constexpr int ND = HALF;
-  static_assert(NV < 32, "lane NV carries L^-1 g");
-  static_assert(!SPLIT || (2 * HALF <= 32 && NV - HALF <= HALF), "split layout");
+  constexpr int KEQ = (WBC_QP_KEQ < HALF ? WBC_QP_KEQ : HALF) < NQ ? (WBC_QP_KEQ < HALF ? WBC_QP_KEQ : HALF) : NQ - 1;
+  static_assert(NQ < 32 && NF >= 0 && NQ >= 2, "lane NQ carries L^-1 g");
+  static_assert(!SPLIT || (2 * HALF <= 32 && NQ - HALF <= HALF), "split layout");
   const int lane = threadIdx.x & 31;
-  const bool act = lane < NV;
+  const bool act = lane < NQ;
+  const bool sfix = NF > 0 && lane >= NQ && lane < NV;   // statically fixed variable
   const bool upper = SPLIT && lane >= 16;    // this lane holds the second half of its row's d vector
   const int crow = SPLIT ? (lane & 15) : lane;
   const bool has_row = crow < nC;
@@ -102,13 +113,20 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   const uint32_t doff = upper ? 8u * HALF : 0u;   // byte offset of this lane's segment inside a broadcast vector
   QpResult res;
   res.status = 0;
-  res.iters = 0;
+  res.iters = NF;
 
-  double hd = act ? hdiag : 0.0;
+  double hd = (lane < NV) ? hdiag : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) hd = fmax(hd, __shfl_xor_sync(WBC_FULL_MASK, hd, o));
   const double piv_min = WBC_QP_PIVOT_REL * fmax(hd, 0.0);
 
+  if (NF > 0) {                              // g_i += sum_k H[i][k] x_k over the statically fixed variables
+#pragma unroll
+    for (int k = NQ; k < NV; ++k) {
+      const double xk = __shfl_sync(WBC_FULL_MASK, lb_in, k);
+      g = fma(h[k], xk, g);
+    }
+  }
   // ---- fixed variables (lb == ub) are eliminated: row/column of H -> identity, g shifted -------------
   // Per-lane bounds live in shared memory during the iterations (lo[0..32) | up[32..64) in `col` once the
   // factorisation is done; row bounds in S.clb / S.cub): registers are the scarce resource of this kernel.
@@ -116,7 +134,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   const bool fixed = (eqb >> lane) & 1u;
   if (eqb) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
+    for (int k = 0; k < NQ; ++k) {
       if ((eqb >> k) & 1u) {                            // warp-uniform
         const double xk = __shfl_sync(WBC_FULL_MASK, lb_in, k);
         g = fma(h[k], xk, g);
@@ -126,15 +144,15 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       }
     }
     if (fixed) g = -lb_in;
-    res.iters = __popc(eqb);
+    res.iters += __popc(eqb);
   }
   __syncwarp();
-  sts_f64(vd_a + 8 * lane, act ? g : 0.0);              // also zeroes the padding vd[NV..32)
+  sts_f64(vd_a + 8 * lane, act ? g : 0.0);              // also zeroes the padding vd[NQ..32)
 
   // ---- phase A: H = L L^T, right-looking; column k of L (lane i holds L[i][k]) is stored to shared memory
   //      (Lc[k][i], 16-byte aligned columns) and broadcast back for the trailing update H[i][j] -= L[i][k] L[j][k]
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
+  for (int k = 0; k < NQ; ++k) {
     double dk = __shfl_sync(WBC_FULL_MASK, h[k], k);
     if (!(dk > piv_min)) {
       dk = piv_min > 0.0 ? piv_min : 1.0;
@@ -149,32 +167,40 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     for (int p = (k + 1) / 2; p < NP; ++p) {
       const double2 l2 = lds_f64x2(R_a + 8 * (k * LC + 2 * p));
       if (2 * p > k) h[WBC_IX(2 * p)] = fma(-lik, l2.x, h[WBC_IX(2 * p)]);
-      if (2 * p + 1 < NV) h[WBC_IX(2 * p + 1)] = fma(-lik, l2.y, h[WBC_IX(2 * p + 1)]);
+      if (2 * p + 1 < NQ) h[WBC_IX(2 * p + 1)] = fma(-lik, l2.y, h[WBC_IX(2 * p + 1)]);
     }
   }
 
   if (SYNC) phase_sync<true>();
   // ---- phase B: forward substitutions L^-1 [I | g | C^T], column-oriented, all right-hand sides at once:
-  //      lane i < NV: e_i (-> row i of J = L^-T), lane NV: g, second array: the rows of C with the fixed
+  //      lane i < NQ: e_i (-> row i of J = L^-T), lane NQ: g, second array: the rows of C with the fixed
   //      variables' coefficients moved into `shift`
-  double Jr[NV], Dr[ND];
+  double Jr[NQ], Dr[ND];
   double shift = 0.0;                                   // sum_k C[c][k] x_k over the fixed variables
   {
     const uint32_t crow_a = S.C + 8 * ((has_row ? crow : 0) * LD) + doff;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int j = 0; j < NQ; ++j) {
       const double gj = lds_f64(vd_a + 8 * j);
-      Jr[j] = (lane == NV) ? gj : ((lane == j) ? 1.0 : 0.0);
+      Jr[j] = (lane == NQ) ? gj : ((lane == j) ? 1.0 : 0.0);
     }
 #pragma unroll
     for (int jl = 0; jl < ND; ++jl) {
       // (a lower lane reads C[c][jl], an upper lane C[c][HALF + jl]; reads past the row are discarded)
       const double cj = lds_f64(crow_a + 8 * jl);
-      Dr[jl] = (has_row && (!upper || jl + HALF < NV)) ? cj : 0.0;
+      Dr[jl] = (has_row && (!upper || jl + HALF < NQ)) ? cj : 0.0;
+    }
+    if (NF > 0) {                                       // statically fixed variables: only the lower lane adds
+#pragma unroll
+      for (int k = NQ; k < NQ + NF; ++k) {
+        const double xk = __shfl_sync(WBC_FULL_MASK, lb_in, k);
+        const double ck = lds_f64(S.C + 8 * ((has_row ? crow : 0) * LD + k));
+        if (has_row && !upper) shift = fma(ck, xk, shift);
+      }
     }
     if (eqb) {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
+      for (int k = 0; k < NQ; ++k) {
         if ((eqb >> k) & 1u) {
           const double xk = __shfl_sync(WBC_FULL_MASK, lb_in, k);
           const bool holder = !SPLIT || (upper == (k >= HALF));
@@ -185,13 +211,13 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
           }
         }
       }
-      if (SPLIT) shift += __shfl_xor_sync(WBC_FULL_MASK, shift, 16);
     }
+    if (SPLIT && (NF > 0 || eqb)) shift += __shfl_xor_sync(WBC_FULL_MASK, shift, 16);
   }
   {
     const uint32_t Lb = R_a + doff;                     // this lane's segment of a column of L
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
+    for (int k = 0; k < NQ; ++k) {
       const double r = lds_f64(rk_a + 8 * k);
       const double yJ = Jr[k] * r;
       Jr[k] = yJ;
@@ -208,7 +234,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       for (int p = (k + 1) / 2; p < NP; ++p) {
         const double2 l2 = lds_f64x2(R_a + 8 * (k * LC + 2 * p));
         if (2 * p > k) Jr[WBC_IX(2 * p)] = fma(-l2.x, yJ, Jr[WBC_IX(2 * p)]);
-        if (2 * p + 1 < NV) Jr[WBC_IX(2 * p + 1)] = fma(-l2.y, yJ, Jr[WBC_IX(2 * p + 1)]);
+        if (2 * p + 1 < NQ) Jr[WBC_IX(2 * p + 1)] = fma(-l2.y, yJ, Jr[WBC_IX(2 * p + 1)]);
       }
       // second array: element jl of a lower lane is column jl, of an upper lane column HALF + jl; elements that
       // only one half updates use a multiplier that is zero in the other half (no per-element selects)
@@ -217,7 +243,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       for (int pl = 0; pl < ND / 2 + (ND & 1); ++pl) {
         const int j0 = 2 * pl, j1 = 2 * pl + 1;
         const bool lv0 = j0 > k, lv1 = j1 > k && j1 < ND;
-        const bool uv0 = SPLIT && (j0 + HALF > k) && (j0 + HALF < NV), uv1 = SPLIT && j1 < ND && (j1 + HALF > k) && (j1 + HALF < NV);
+        const bool uv0 = SPLIT && (j0 + HALF > k) && (j0 + HALF < NQ), uv1 = SPLIT && j1 < ND && (j1 + HALF > k) && (j1 + HALF < NQ);
         if (!(lv0 || lv1 || uv0 || uv1)) continue;
         const double2 l2 = lds_f64x2(Lb + 8 * (k * LC + 2 * pl));
         if (lv0 || uv0) Dr[WBC_DX(j0)] = fma(-l2.x, (lv0 && (uv0 || !SPLIT)) ? yD : (lv0 ? yD_lo : yD_up), Dr[WBC_DX(j0)]);
@@ -233,7 +259,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   {
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
+    for (int j = 0; j < NQ; ++j) {
       if (j & 1) a1 = fma(Jr[j], Jr[j], a1);
       else a0 = fma(Jr[j], Jr[j], a0);
     }
@@ -249,14 +275,14 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     if (!SPLIT || lane < 16) sts_f64(S.dd + 8 * (32 + lane), ddD);
     sts_f64(lo_a + 8 * lane, lb_in);
     sts_f64(up_a + 8 * lane, ub_in);
-    if (lane == NV) publish_row<NV>(vd_a, Jr);
+    if (lane == NQ) publish_row<NQ>(vd_a, Jr);
     __syncwarp();
     double x0 = 0.0, x1 = 0.0, c0 = 0.0, c1 = 0.0;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       const double2 w2 = lds_f64x2(vd_a + 16 * p);
       x0 = fma(-Jr[2 * p], w2.x, x0);
-      if (2 * p + 1 < NV) x1 = fma(-Jr[WBC_IX(2 * p + 1)], w2.y, x1);
+      if (2 * p + 1 < NQ) x1 = fma(-Jr[WBC_IX(2 * p + 1)], w2.y, x1);
     }
 #pragma unroll
     for (int p = 0; p < (ND + 1) / 2; ++p) {
@@ -264,7 +290,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       c0 = fma(-Dr[2 * p], w2.x, c0);
       if (2 * p + 1 < ND) c1 = fma(-Dr[WBC_DX(2 * p + 1)], w2.y, c1);
     }
-    x = fixed ? lb_in : (x0 + x1);
+    x = (fixed || sfix) ? lb_in : (x0 + x1);
     double cx = c0 + c1;
     if (SPLIT) cx += __shfl_xor_sync(WBC_FULL_MASK, cx, 16);
     ax = cx + shift;
@@ -275,10 +301,116 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   int iq = 0, p_eq = 0;
   int ws_c = -1, slot = lane;                // per working-set position (lane = position)
   double u = 0.0, rinv = 0.0;
-  int bstat = fixed ? 3 : 0, cstat = 0;      // 0 none 1 lower 2 upper 3 eq
+  int bstat = (fixed || sfix) ? 3 : 0, cstat = 0;      // 0 none 1 lower 2 upper 3 eq
   unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && lds_f64(S.clb + 8 * lane) == lds_f64(S.cub + 8 * lane));
 
   // ---- equality rows first, in index order: no step-length logic, no multipliers, no column of R, no d1 ----
+  // The first KEQ accepted rows each have a straight-line block of their own: the position K in the working set is a
+  // compile-time constant, so the passes run over the live entries [K, NQ) only (no zero padding), column K of J
+  // and of the rows' d vectors is a plain register (no switch), and column K is not updated at all: columns
+  // [0, p_eq) are never read again once their reflector has been applied (the dual step and the Givens
+  // rotations only touch the inequality block).
+  {
+    bool eq_more = eq_mask_row != 0;
+#pragma unroll
+    for (int K = 0; K < KEQ; ++K) {
+      if (eq_more) {                                                  // warp-uniform
+        bool placed = false;
+#pragma unroll 1
+        while (!placed && eq_mask_row) {
+          const int c = __ffs(eq_mask_row) - 1;
+          eq_mask_row &= eq_mask_row - 1;
+          res.iters++;
+          if (crow == c) {
+            publish_row<ND>(vd_a + doff, Dr);                          // SPLIT: both halves write their segment
+            if (SPLIT && !upper) {                                     // dead entries [0, K) read as zeros by the lower lanes
+#pragma unroll
+              for (int p = 0; p < K / 2; ++p) sts_f64x2(vd_a + 16 * p, 0.0, 0.0);
+              if (K & 1) sts_f64(vd_a + 8 * (K - 1), 0.0);
+            }
+          }
+          __syncwarp();
+          double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+          for (int p = K / 2; p < NP; ++p) {
+            const double2 d2 = lds_f64x2(vd_a + 16 * p);
+            if (2 * p >= K) {
+              z0 = fma(Jr[2 * p], d2.x, z0);
+              e0 = fma(d2.x, d2.x, e0);
+              if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+            }
+            if (2 * p + 1 < NQ) {
+              z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
+              e1 = fma(d2.y, d2.y, e1);
+              if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+            }
+          }
+          if (SPLIT) {                                                // K <= HALF: the upper lanes use all their entries
+#pragma unroll
+            for (int p = 0; p < ND / 2; ++p) {
+              const double2 d2 = lds_f64x2(vd_a + doff + 16 * p);
+              w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+              w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
+            }
+          }
+          double w = w0 + w1;
+          if (SPLIT) w += __shfl_xor_sync(WBC_FULL_MASK, w, 16);
+          const double z = z0 + z1, dd2 = e0 + e1;
+          const double s_c = __shfl_sync(WBC_FULL_MASK, ax, c) - lds_f64(S.clb + 8 * c);     // C_c x - bound
+          if (dd2 <= WBC_QP_DEP_TOL * lds_f64(S.dd + 8 * (32 + c))) {      // redundant (or inconsistent) equality
+            if (fabs(s_c) > 1e-8) res.status |= WBC_QP_INFEASIBLE;
+            __syncwarp();
+            continue;
+          }
+          const double rs = fast_rsqrt(dd2);
+          const double t = -s_c * (rs * rs);
+          x = fma(t, z, x);
+          ax = fma(t, w, ax);
+          const double d_iq = lds_f64(vd_a + 8 * K);
+          const double nrm = dd2 * rs;
+          const double sigma = (d_iq >= 0.0) ? nrm : -nrm;
+          const double isig = (d_iq >= 0.0) ? rs : -rs;
+          const double beta = isig * fast_rcp(d_iq + sigma);
+          double diq;
+          if (!SPLIT) diq = Dr[WBC_DX(K)];
+          else {                                                      // K < HALF: column K sits in the lower lanes
+            diq = upper ? 0.0 : Dr[WBC_DX(K)];
+            diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
+          }
+          const double nbJ = -beta * fma(sigma, Jr[K], z);
+          const double nbD = -beta * fma(sigma, diq, w);
+#pragma unroll
+          for (int p = (K + 1) / 2; p < NP; ++p) {                    // v_j = d_j for j > K
+            const double2 v2 = lds_f64x2(vd_a + 16 * p);
+            if (2 * p > K) {
+              Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
+              if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+            }
+            if (2 * p + 1 < NQ) {
+              Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
+              if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
+            }
+          }
+          if (SPLIT) {
+#pragma unroll
+            for (int p = 0; p < ND / 2; ++p) {
+              const double2 v2 = lds_f64x2(vd_a + doff + 16 * p);
+              // (entry K of a lower lane picks up nbD * d_K: column K is dead from here on)
+              Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+              Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
+            }
+          }
+          if (lane == c) cstat = 3;          // (no multiplier, 1 / R_KK or constraint id: equality positions are never dropped)
+          placed = true;
+          __syncwarp();
+        }
+        if (placed) iq = K + 1;
+        else eq_more = false;
+      }
+    }
+    p_eq = iq;
+  }
+  // any further equality rows: one rolled loop, run-time position
 #pragma unroll 1
   while (eq_mask_row) {
     const int c = __ffs(eq_mask_row) - 1;
@@ -295,7 +427,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       z0 = fma(Jr[2 * p], d2.x, z0);
       e0 = fma(d2.x, d2.x, e0);
       if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
-      if (2 * p + 1 < NV) {
+      if (2 * p + 1 < NQ) {
         z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
         e1 = fma(d2.y, d2.y, e1);
         if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
@@ -330,7 +462,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     const double beta = isig * fast_rcp(v_iq);
     double jiq = 0.0, diq = 0.0;
     switch (iq) {
-#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; \
+#define WBC_PK(j) case (j): if ((j) < NQ) { jiq = Jr[WBC_IX(j)]; \
         if (!SPLIT) diq = Dr[WBC_DX(j)]; \
         else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
         else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
@@ -348,7 +480,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       const double2 v2 = lds_f64x2(vd_a + 16 * p);
       Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
       if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
-      if (2 * p + 1 < NV) {
+      if (2 * p + 1 < NQ) {
         Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
         if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
       }
@@ -412,7 +544,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     res.iters++;
     // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
     if (is_box) {
-      if (lane == owner) publish_row<NV>(vd_a, Jr);
+      if (lane == owner) publish_row<NQ>(vd_a, Jr);
     } else {
       if (crow == owner) publish_row<ND>(vd_a + doff, Dr);         // SPLIT: both halves write their segment
     }
@@ -429,7 +561,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       z0 = fma(Jr[2 * p], d2.x, z0);
       e0 = fma(d2.x, d2.x, e0);
       if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
-      if (2 * p + 1 < NV) {
+      if (2 * p + 1 < NQ) {
         z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
         e1 = fma(d2.y, d2.y, e1);
         if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
@@ -511,7 +643,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
           }
           // rotate columns k, k + 1 of J and of the rows' d vectors
           switch (k) {
-#define WBC_GV(j) case (j): if ((j) + 1 < NV) { \
+#define WBC_GV(j) case (j): if ((j) + 1 < NQ) { \
               const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)]; \
               Jr[WBC_IX(j)] = cg * j0 + sg * j1; Jr[WBC_IX((j) + 1)] = -sg * j0 + cg * j1; \
               if (!SPLIT || (j) + 1 < HALF) { \
@@ -557,7 +689,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       const double beta = isig * fast_rcp(v_iq);                      // 1 / (sigma v_iq)
       double jiq = 0.0, diq = 0.0;
       switch (iq) {                                                   // column iq of J and of the rows' d vectors
-#define WBC_PK(j) case (j): if ((j) < NV) { jiq = Jr[WBC_IX(j)]; \
+#define WBC_PK(j) case (j): if ((j) < NQ) { jiq = Jr[WBC_IX(j)]; \
           if (!SPLIT) diq = Dr[WBC_DX(j)]; \
           else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
           else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
@@ -575,7 +707,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
         const double2 v2 = lds_f64x2(vd_a + 16 * p);
         Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
         if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
-        if (2 * p + 1 < NV) {
+        if (2 * p + 1 < NQ) {
           Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
           if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
         }
@@ -608,7 +740,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     __syncwarp();
   }
 
-  x_out = fixed ? lds_f64(lo_a + 8 * lane) : x;
-  pack_active_sets(lane, n, nC, bstat, cstat, res);
+  x_out = (fixed || sfix) ? lds_f64(lo_a + 8 * lane) : x;
+  pack_active_sets(lane, NQ + NF, nC, bstat, cstat, res);
   return res;
 }

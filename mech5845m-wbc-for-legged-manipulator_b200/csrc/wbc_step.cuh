@@ -435,7 +435,8 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 // apart each stream the whole code from L2 on their own (measured: 2.4x slower without the barriers); in step,
 // one fetch feeds all warps.  Padding warps shadow the last state (no writes) so the barriers stay uniform.
 // Shared memory is addressed through 32-bit shared-window addresses (wbc_device.cuh: smem_addr, lds_*, sts_*).
-template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD>
+// NF: the last NF velocity DoFs are locked by the configuration (gripper + fingers, lb = ub = 0): the QP runs on NV - NF variables
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0>
 __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws, const StepLayout L) {
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
   constexpr int LD = NV | 1;
@@ -865,13 +866,13 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     {
       double h[NV];
 #pragma unroll
-      for (int l = 0; l < NV; ++l) h[l] = (lane < NV) ? lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0) : 0.0;
+      for (int l = 0; l < NV; ++l) h[l] = (lane < NV - NF) ? lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0) : 0.0;
       const double hdiag = (lane < NV) ? lds_f64(hrow_a + 8 * lane) + aj * aj : 0.0;
       __syncwarp();                    // Hs becomes the solver's R factor
       QpRegShared S;
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
       S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
-      res = warp_qp_solve_reg<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0)>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
+      res = warp_qp_solve_reg<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
     }
 
     phase_sync<PS>();            // (measured: dropping this barrier costs 6 %)
