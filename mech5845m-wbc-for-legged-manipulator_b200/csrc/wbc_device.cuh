@@ -19,9 +19,11 @@
 
 // Device copy of the kinematic tree (built on the host from WbcTreeTable, lives in global memory,
 // staged into shared memory once per CTA).
+#define WBC_FK_ROUNDS 5       // 2^5 >= WBC_MAX_JOINTS
 struct DevModel {
-  int32_t njoints, nq, nv, nframes, maxdepth, pad0, pad1, pad2;
+  int32_t njoints, nq, nv, nframes, maxdepth, nrounds, pad1, pad2;
   int32_t parent[WBC_MAX_JOINTS];
+  int32_t anc[WBC_FK_ROUNDS][WBC_MAX_JOINTS];   // anc[r][j]: the 2^r-th ancestor of joint j (0 = none): FK by pointer jumping
   int32_t jtype[WBC_MAX_JOINTS];
   int32_t idx_q[WBC_MAX_JOINTS];
   int32_t depth[WBC_MAX_JOINTS];

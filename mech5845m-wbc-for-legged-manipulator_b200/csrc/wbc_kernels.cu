@@ -53,15 +53,20 @@ template <bool SPLIT> struct StepWarps {
   static constexpr int ctas = SPLIT ? WBC_STEP_CTAS : 1;
 };
 
+#ifdef WBC_STEP_MAXNREG       // A/B builds: explicit register cap instead of the launch-bounds heuristic
+#define WBC_STEP_BOUNDS(SPLIT) __maxnreg__(WBC_STEP_MAXNREG)
+#else
+#define WBC_STEP_BOUNDS(SPLIT) __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>::ctas)
+#endif
 template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF>
-__global__ void __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>::ctas) wbc_step_kernel(const __grid_constant__ StepParams P) {
+__global__ void WBC_STEP_BOUNDS(SPLIT) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
   stage_model(P.model, Ms);
-  const StepLayout L = step_layout(NV, P.nC);
+  constexpr StepLayout L = step_layout(NV);
   const int warp = threadIdx.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
-  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF>(P, Ms, ws, L);
+  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF>(P, Ms, ws);
 }
 
 // FK + frame Jacobians accessor (HBM-write bound): one state per warp
@@ -456,6 +461,11 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
     m->total_mass += t->mass[j];
   }
   m->maxdepth = maxd;
+  m->nrounds = 0;
+  while ((1 << m->nrounds) < maxd) ++m->nrounds;       // 2^nrounds >= depth of the deepest joint
+  for (int j = 0; j < WBC_MAX_JOINTS; ++j) m->anc[0][j] = (j > 0 && j < t->njoints) ? t->parent[j] : 0;
+  for (int r = 1; r < WBC_FK_ROUNDS; ++r)
+    for (int j = 0; j < WBC_MAX_JOINTS; ++j) m->anc[r][j] = m->anc[r - 1][m->anc[r - 1][j]];
   for (int k = 0; k < WBC_MAX_NV; ++k) m->col_q[k] = -1;
   for (int j = 1; j < t->njoints; ++j) {
     const int iv = t->idx_v[j];
@@ -503,7 +513,7 @@ static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15);
 
 template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0>
 static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
-  const StepLayout L = step_layout(NV, P.nC);
+  constexpr StepLayout L = step_layout(NV);
   const size_t per_warp = (size_t)L.total * sizeof(double);
   int max_optin = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, model->device));
@@ -568,6 +578,7 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   P->io = *io;
   memset(&P->dbg, 0, sizeof(P->dbg));
   P->nC = cfg_nc(*cfg);
+  set_rows(P);
   P->m_rows = cfg_m(*cfg, model->host.nv);
   P->flags = (int)io->flags & ~WBC_STEP_FLAG_WEIGHTS_IDENTITY;
   {
@@ -731,6 +742,7 @@ int wbc_step_launch_info(const WbcModel* model, int32_t* grid, int32_t* block, i
   memset(&P, 0, sizeof(P));
   P.nC = 16;
   P.N = 1 << 20;
+  P.cfg.gripper_joint_id = model->host.nv - 7;   // the shipped arms: gripper + two fingers locked (the NF = 3 instantiation)
   int info[4] = {0, 0, 0, 0};
   int rc = launch_step<false>(model, P, nullptr, info);
   if (rc != WBC_OK) return rc;

@@ -38,9 +38,11 @@ struct StepLayout {   // per-warp shared-memory layout in doubles (every offset 
 __host__ __device__ inline int wbc_ld(int nv) { return nv | 1; }
 #define WBC_LDT 38    // doubles per column of the transposed task rows: 304 B = 19 x 16 B, conflict-free 128-bit accesses
 
-__host__ __device__ inline StepLayout step_layout(int nv, int nC) {
-  StepLayout L;
-  const int ld = wbc_ld(nv);
+// (sized for WBC_MAX_NC rows whatever the configuration: the layout is a compile-time constant of the kernel, so every
+//  shared-memory address of the tick is [per-warp base + immediate])
+__host__ __device__ constexpr StepLayout step_layout(int nv, int nC = WBC_MAX_NC) {
+  StepLayout L{};
+  const int ld = nv | 1;
   int r0 = nv * (nv + 2);                              // H rows, later the L columns / R factor of the QP ...
   const int fk = WBC_MAX_JOINTS * WBC_T_STRIDE;        // ... aliased by the oMi scratch (dead before H is written)
   if (r0 < fk) r0 = fk;
@@ -66,7 +68,22 @@ struct StepParams {
   WbcAssembleOut dbg;
   long long N;
   int nC, m_rows, flags;
+  int row_com, row_trunk, row_ee[5], row_extra;   // first row of each constraint block in C (-1: off), set_rows()
 };
+
+// Row layout of C implied by the constraint mask (findConstraints order, Robot_Wrapper4.py:764-836): computed once on
+// the host so that the kernel reads the offsets straight from the parameter bank.
+inline void set_rows(StepParams* P) {
+  int nrows = 0;
+  P->row_com = P->row_trunk = -1;
+  if (P->cfg.constraint_mask & WBC_CON_COM) { P->row_com = nrows; nrows += 2; }
+  if (P->cfg.constraint_mask & WBC_CON_TRUNK) { P->row_trunk = nrows; nrows += 4; }
+  for (int i = 0; i < 5; ++i) {
+    P->row_ee[i] = -1;
+    if (P->cfg.constraint_mask & (WBC_CON_FR << i)) { P->row_ee[i] = nrows; nrows += 3; }
+  }
+  P->row_extra = nrows;
+}
 
 // Number of rows of C and A implied by the masks.
 __host__ __device__ inline int cfg_nc(const WbcConfig& c) {
@@ -158,17 +175,17 @@ __device__ __forceinline__ void prefetch_inputs(const WbcStepIO& io, long long s
 
 #define WBC_MOFF(f) ((uint32_t)offsetof(DevModel, f))
 
-// forwardKinematics into shared memory (stride WBC_T_STRIDE), level by level; 32-bit shared addressing.
+#ifndef WBC_FK_SCAN
+#define WBC_FK_SCAN 1
+#endif
+// forwardKinematics into shared memory (stride WBC_T_STRIDE); 32-bit shared addressing.
 __device__ __forceinline__ void warp_fk_a(uint32_t M_a, uint32_t q_a, uint32_t oMi_a, int lane) {
   double Rl[9], pl[3];
-  int myDepth = 0, par = 0;
   const int nj = lds_s32(M_a + WBC_MOFF(njoints));
   const bool active = lane >= 1 && lane < nj;
   if (active) {
     const int jt = lds_s32(M_a + WBC_MOFF(jtype) + 4 * lane);
     const int iq = lds_s32(M_a + WBC_MOFF(idx_q) + 4 * lane);
-    par = lds_s32(M_a + WBC_MOFF(parent) + 4 * lane);
-    myDepth = lds_s32(M_a + WBC_MOFF(depth) + 4 * lane);
     const bool ident = lds_s32(M_a + WBC_MOFF(pl_ident) + 4 * lane) != 0;
     const uint32_t qa = q_a + 8 * iq;
     double Rj[9], pj[3] = {0.0, 0.0, 0.0}, plp[3];
@@ -202,29 +219,69 @@ __device__ __forceinline__ void warp_fk_a(uint32_t M_a, uint32_t q_a, uint32_t o
     if (jt == WBC_JT_REVOLUTE) { pl[0] = plp[0]; pl[1] = plp[1]; pl[2] = plp[2]; }   // (placement * 0 + p, exactly p)
     else { pl[0] += plp[0]; pl[1] += plp[1]; pl[2] += plp[2]; }
   }
-  const int maxdepth = lds_s32(M_a + WBC_MOFF(maxdepth));
-  const uint32_t out_a = oMi_a + 8 * WBC_T_STRIDE * lane;
-  for (int d = 1; d <= maxdepth; ++d) {
-    if (active && myDepth == d) {
-      if (par == 0) {
+#if !WBC_FK_SCAN
+  {
+    const int par = active ? lds_s32(M_a + WBC_MOFF(parent) + 4 * lane) : 0;
+    const int myDepth = active ? lds_s32(M_a + WBC_MOFF(depth) + 4 * lane) : 0;
+    const int maxdepth = lds_s32(M_a + WBC_MOFF(maxdepth));
+    const uint32_t out_a = oMi_a + 8 * WBC_T_STRIDE * lane;
+    for (int d = 1; d <= maxdepth; ++d) {
+      if (active && myDepth == d) {
+        if (par == 0) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, Rl[i]);
-        sts_f64(out_a + 72, pl[0]); sts_f64(out_a + 80, pl[1]); sts_f64(out_a + 88, pl[2]);
-      } else {
-        const uint32_t pa = oMi_a + 8 * WBC_T_STRIDE * par;
-        double Rp[9], R[9], p[3], pp[3];
-        lds_mat3(pa, Rp);
-        lds_vec3(pa + 72, pp);
-        mat3_mul(Rp, Rl, R);
-        mat3_vec(Rp, pl, p);
+          for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, Rl[i]);
+          sts_f64(out_a + 72, pl[0]); sts_f64(out_a + 80, pl[1]); sts_f64(out_a + 88, pl[2]);
+        } else {
+          const uint32_t pa = oMi_a + 8 * WBC_T_STRIDE * par;
+          double Rp[9], R[9], p[3], pp[3];
+          lds_mat3(pa, Rp);
+          lds_vec3(pa + 72, pp);
+          mat3_mul(Rp, Rl, R);
+          mat3_vec(Rp, pl, p);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, R[i]);
-        sts_f64(out_a + 72, p[0] + pp[0]); sts_f64(out_a + 80, p[1] + pp[1]); sts_f64(out_a + 88, p[2] + pp[2]);
+          for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, R[i]);
+          sts_f64(out_a + 72, p[0] + pp[0]); sts_f64(out_a + 80, p[1] + pp[1]); sts_f64(out_a + 88, p[2] + pp[2]);
+        }
       }
+      __syncwarp();
     }
+  }
+}
+#else
+  // oMi[j] = liMi[root] ... liMi[parent(j)] liMi[j] by pointer jumping: after round r every joint holds the product
+  // over its 2^(r+1) nearest ancestors (itself included), so ceil(log2(depth)) rounds replace `depth` serial levels and
+  // every lane works in every round.  The own transform stays in registers; only the ancestor's comes from shared
+  // memory.  (The association order of the products differs from Pinocchio's root-to-leaf sweep: rounding-level, 1e-16.)
+  // Divergence-free: slot 0 (the universe) and the slots of the idle lanes hold the identity, and a joint without a
+  // 2^r-th ancestor composes with slot 0 (1 * x + 0 * y + 0 * z is exact), so all 32 lanes run the same code.
+  const uint32_t out_a = oMi_a + 8 * WBC_T_STRIDE * lane;
+  if (!active) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rl[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    pl[0] = pl[1] = pl[2] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, Rl[i]);
+  sts_f64(out_a + 72, pl[0]); sts_f64(out_a + 80, pl[1]); sts_f64(out_a + 88, pl[2]);
+  __syncwarp();
+  const int nrounds = lds_s32(M_a + WBC_MOFF(nrounds));
+#pragma unroll 1
+  for (int r = 0; r < nrounds; ++r) {
+    const uint32_t pa = oMi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(anc) + 4 * (WBC_MAX_JOINTS * r + lane));
+    double Rp[9], pp[3], R[9], p[3];
+    lds_mat3(pa, Rp);
+    lds_vec3(pa + 72, pp);
+    __syncwarp();                      // every ancestor has been read before anyone overwrites its slot
+    mat3_mul(Rp, Rl, R);
+    mat3_vec(Rp, pl, p);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { Rl[i] = R[i]; sts_f64(out_a + 8 * i, R[i]); }
+    pl[0] = p[0] + pp[0]; pl[1] = p[1] + pp[1]; pl[2] = p[2] + pp[2];
+    sts_f64(out_a + 72, pl[0]); sts_f64(out_a + 80, pl[1]); sts_f64(out_a + 88, pl[2]);
     __syncwarp();
   }
 }
+#endif
 
 // velDamperJointConstraints (Robot_Wrapper4.py:572-637) for velocity index k.
 __device__ __forceinline__ void damper_bounds_a(uint32_t M_a, const WbcConfig& cfg, uint32_t q_a, int k, double& lbv,
@@ -437,7 +494,8 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 // Shared memory is addressed through 32-bit shared-window addresses (wbc_device.cuh: smem_addr, lds_*, sts_*).
 // NF: the last NF velocity DoFs are locked by the configuration (gripper + fingers, lb = ub = 0): the QP runs on NV - NF variables
 template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0>
-__device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws, const StepLayout L) {
+__device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws) {
+  constexpr StepLayout L = step_layout(NV);
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
   constexpr int LD = NV | 1;
   constexpr int nq = NV + 1;
@@ -456,17 +514,12 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
   const uint32_t clb_a = vd_a + 8 * 32, cub_a = clb_a + 8 * 32, bs_a = cub_a + 8 * 32;
   const uint32_t in0_a = ws_a + 8 * L.in;
 
-  // row layout of C (uniform over the launch)
-  int row_com = -1, row_trunk = -1, row_ee[5], nrows = 0;
-  if (cfg.constraint_mask & WBC_CON_COM) { row_com = nrows; nrows += 2; }
-  if (cfg.constraint_mask & WBC_CON_TRUNK) { row_trunk = nrows; nrows += 4; }
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    row_ee[i] = -1;
-    if (cfg.constraint_mask & (WBC_CON_FR << i)) { row_ee[i] = nrows; nrows += 3; }
-  }
-  const int row_extra = nrows;
-  const int nC = nrows + cfg.n_extra_rows;
+  // row layout of C (uniform over the launch; parameter bank)
+#define row_com P.row_com
+#define row_trunk P.row_trunk
+#define row_ee P.row_ee
+#define row_extra P.row_extra
+  const int nC = P.nC;
   const bool joint_on = (cfg.task_mask & WBC_TASK_JOINT) != 0;
   const double aj = joint_on ? (1.0 / NV) * cfg.joint_task_weight : 0.0;       // qpJointA (:1199-1206)
   const bool w_ident = (P.flags & WBC_STEP_FLAG_WEIGHTS_IDENTITY) != 0;        // every 6x6 task weight is the identity
@@ -958,4 +1011,8 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     buf ^= 1;
   }
   cp_async_wait_all();
+#undef row_com
+#undef row_trunk
+#undef row_ee
+#undef row_extra
 }

@@ -1,4 +1,9 @@
+# A/B of library builds under build_variants/ (WBC_B200_LIB override): bash tools/ab.sh name1 name2 ...
 for v in "$@"; do
-  WBC_B200_LIB=$PWD/build_variants/libwbc_$v.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>gpurun_out/ab_err.log | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$v', round(d['value']/1e6,2), 'M/s e2e', round(d['e2e']['value']/1e6,2), d['launch'], d['verified'])"
+  WBC_B200_LIB=$PWD/build_variants/libwbc_$v.so python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/ab_err_$v.log | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print('$v', round(d['value']/1e6,2), 'M/s e2e', round(d['e2e']['value']/1e6,2), d['launch'], d['verified'])
+except Exception as e:
+    print('$v', 'FAILED', e)"
 done
