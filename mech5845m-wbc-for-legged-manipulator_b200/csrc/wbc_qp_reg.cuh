@@ -71,10 +71,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
 #define WBC_DX(j) (((j) >= 0 && (j) < ND) ? (j) : 0)
 
 // the calling lane publishes N register values as a[0..N) at shared address `a0` (zero padded to an even count)
-template <int N>
+template <int V> struct QpIntC { static constexpr int value = V; };
+template <int N, int START = 0>
 __device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
 #pragma unroll
-  for (int p = 0; p < (N + 1) / 2; ++p)
+  for (int p = START / 2; p < (N + 1) / 2; ++p)
     sts_f64x2(a0 + 16 * p, a[2 * p], (2 * p + 1 < N) ? a[(2 * p + 1 < N) ? 2 * p + 1 : 0] : 0.0);
 }
 
@@ -506,6 +507,10 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   bool have = false, is_box = false;
   int ip = 0, side = -1, owner = 0;
   double sgn = 1.0, dd = 0.0, u_new = 0.0;
+  // The loop body is instantiated twice: P0 is a compile-time lower bound of the live columns of J and of the rows' d
+  // vectors.  With the usual KEQ equality rows in the working set the passes run over columns [KEQ, NQ) only.
+  auto ineq_loop = [&](auto P0c) {
+  constexpr int P0 = decltype(P0c)::value;
 #pragma unroll 1
   for (;;) {
     if (!have) {
@@ -544,7 +549,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     res.iters++;
     // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
     if (is_box) {
-      if (lane == owner) publish_row<NQ>(vd_a, Jr);
+      if (lane == owner) publish_row<NQ, P0>(vd_a, Jr);
     } else {
       if (crow == owner) publish_row<ND>(vd_a + doff, Dr);         // SPLIT: both halves write their segment
     }
@@ -556,11 +561,13 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     // z = J2 d2, w = D2 d2 (= C z), dd2 = |d2|^2
     double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
+    for (int p = P0 / 2; p < NP; ++p) {
       const double2 d2 = lds_f64x2(vd_a + 16 * p);
-      z0 = fma(Jr[2 * p], d2.x, z0);
-      e0 = fma(d2.x, d2.x, e0);
-      if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+      if (2 * p >= P0) {
+        z0 = fma(Jr[2 * p], d2.x, z0);
+        e0 = fma(d2.x, d2.x, e0);
+        if (!SPLIT) w0 = fma(Dr[WBC_DX(2 * p)], d2.x, w0);
+      }
       if (2 * p + 1 < NQ) {
         z1 = fma(Jr[WBC_IX(2 * p + 1)], d2.y, z1);
         e1 = fma(d2.y, d2.y, e1);
@@ -643,7 +650,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
           }
           // rotate columns k, k + 1 of J and of the rows' d vectors
           switch (k) {
-#define WBC_GV(j) case (j): if ((j) + 1 < NQ) { \
+#define WBC_GV(j) case (j): if ((j) >= P0 && (j) + 1 < NQ) { \
               const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)]; \
               Jr[WBC_IX(j)] = cg * j0 + sg * j1; Jr[WBC_IX((j) + 1)] = -sg * j0 + cg * j1; \
               if (!SPLIT || (j) + 1 < HALF) { \
@@ -689,7 +696,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       const double beta = isig * fast_rcp(v_iq);                      // 1 / (sigma v_iq)
       double jiq = 0.0, diq = 0.0;
       switch (iq) {                                                   // column iq of J and of the rows' d vectors
-#define WBC_PK(j) case (j): if ((j) < NQ) { jiq = Jr[WBC_IX(j)]; \
+#define WBC_PK(j) case (j): if ((j) >= P0 && (j) < NQ) { jiq = Jr[WBC_IX(j)]; \
           if (!SPLIT) diq = Dr[WBC_DX(j)]; \
           else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
           else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
@@ -703,10 +710,12 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);                    // vd = v = d2 + sigma e_iq (zeros below iq)
       __syncwarp();
 #pragma unroll
-      for (int p = 0; p < NP; ++p) {
+      for (int p = P0 / 2; p < NP; ++p) {
         const double2 v2 = lds_f64x2(vd_a + 16 * p);
-        Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
-        if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+        if (2 * p >= P0) {
+          Jr[2 * p] = fma(nbJ, v2.x, Jr[2 * p]);
+          if (!SPLIT) Dr[WBC_DX(2 * p)] = fma(nbD, v2.x, Dr[WBC_DX(2 * p)]);
+        }
         if (2 * p + 1 < NQ) {
           Jr[WBC_IX(2 * p + 1)] = fma(nbJ, v2.y, Jr[WBC_IX(2 * p + 1)]);
           if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
@@ -739,6 +748,9 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     }
     __syncwarp();
   }
+  };
+  if (KEQ >= 2 && p_eq == KEQ) ineq_loop(QpIntC<(KEQ & ~1)>{});
+  else ineq_loop(QpIntC<0>{});
 
   x_out = (fixed || sfix) ? lds_f64(lo_a + 8 * lane) : x;
   pack_active_sets(lane, NQ + NF, nC, bstat, cstat, res);
