@@ -76,6 +76,11 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
+// predicated store: `if (c) sts_f64(a, v)` compiles to a branch around the (volatile) store with a convergence
+// barrier (BSSY / BRA / STS / BSYNC); this is a compare and one predicated STS
+__device__ __forceinline__ void sts_f64_if(bool c, uint32_t a, double v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(a), "d"(v), "r"((int)c) : "memory");
+}
 __device__ __forceinline__ int lds_s32(uint32_t a) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));

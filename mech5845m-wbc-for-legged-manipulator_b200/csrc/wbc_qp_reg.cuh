@@ -161,8 +161,10 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     }
     const double r = fast_rsqrt(dk);
     const double lik = h[k] * r;
-    if (lane < LC) sts_f64(R_a + 8 * (k * LC + lane), lik);
-    if (lane == 0) sts_f64(rk_a + 8 * k, r);
+    // unpredicated stores: lanes >= LC write zeros (h is 0 there) into the head of column k + 1, which is written
+    // after this one; r is uniform
+    sts_f64(R_a + 8 * (k * LC + lane), lik);
+    sts_f64(rk_a + 8 * k, r);
     __syncwarp();
 #pragma unroll
     for (int p = (k + 1) / 2; p < NP; ++p) {
@@ -273,7 +275,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     if (SPLIT) ddD += __shfl_xor_sync(WBC_FULL_MASK, ddD, 16);
     __syncwarp();
     sts_f64(S.dd + 8 * lane, a0 + a1);
-    if (!SPLIT || lane < 16) sts_f64(S.dd + 8 * (32 + lane), ddD);
+    sts_f64_if(!SPLIT || lane < 16, S.dd + 8 * (32 + lane), ddD);
     sts_f64(lo_a + 8 * lane, lb_in);
     sts_f64(up_a + 8 * lane, ub_in);
     if (lane == NQ) publish_row<NQ>(vd_a, Jr);
@@ -419,7 +421,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     res.iters++;
     if (crow == c) publish_row<ND>(vd_a + doff, Dr);                 // SPLIT: both halves write their segment
     __syncwarp();
-    if (lane < iq) sts_f64(vd_a + 8 * lane, 0.0);
+    sts_f64_if(lane < iq, vd_a + 8 * lane, 0.0);
     __syncwarp();
     double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
@@ -474,7 +476,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     if (SPLIT) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
     const double nbJ = -beta * fma(sigma, jiq, z);
     const double nbD = -beta * fma(sigma, diq, w);
-    if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);
+    sts_f64_if(lane == 0, vd_a + 8 * iq, v_iq);
     __syncwarp();
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -556,7 +558,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     __syncwarp();
     const double d_own = lds_f64(vd_a + 8 * lane);
     __syncwarp();
-    if (lane < iq) sts_f64(vd_a + 8 * lane, 0.0);
+    sts_f64_if(lane < iq, vd_a + 8 * lane, 0.0);
     __syncwarp();
     // z = J2 d2, w = D2 d2 (= C z), dd2 = |d2|^2
     double z0 = 0.0, z1 = 0.0, w0 = 0.0, w1 = 0.0, e0 = 0.0, e1 = 0.0;
@@ -707,7 +709,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       if (SPLIT) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
       const double nbJ = -beta * fma(sigma, jiq, z);
       const double nbD = -beta * fma(sigma, diq, w);
-      if (lane == 0) sts_f64(vd_a + 8 * iq, v_iq);                    // vd = v = d2 + sigma e_iq (zeros below iq)
+      sts_f64_if(lane == 0, vd_a + 8 * iq, v_iq);                    // vd = v = d2 + sigma e_iq (zeros below iq)
       __syncwarp();
 #pragma unroll
       for (int p = P0 / 2; p < NP; ++p) {
@@ -731,8 +733,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
       }
       if (!is_eq) {                                                   // R column (signed): [d1 ; -sigma]
         const int slot_new = __shfl_sync(WBC_FULL_MASK, slot, iq);
-        if (lane < iq) sts_f64(R_a + 8 * (lane * LD + slot_new), sgn * d_own);
-        if (lane == iq) sts_f64(R_a + 8 * (iq * LD + slot_new), -sgn * sigma);
+        sts_f64_if(lane < iq, R_a + 8 * (lane * LD + slot_new), sgn * d_own);
+        sts_f64_if(lane == iq, R_a + 8 * (iq * LD + slot_new), -sgn * sigma);
       }
       if (lane == iq) {
         rinv = -sgn * isig;                                           // 1 / R_iq,iq

@@ -816,7 +816,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
         double h0 = fma(a[6 * t], v0.x, hprev), h1 = a[6 * t + 1] * v0.y;
         h0 = fma(a[6 * t + 2], v1.x, h0); h1 = fma(a[6 * t + 3], v1.y, h1);
         h0 = fma(a[6 * t + 4], v2.x, h0); h1 = fma(a[6 * t + 5], v2.y, h1);
-        if (lane < NV) sts_f64(ha, h0 + h1);
+        sts_f64_if(lane < NV, ha, h0 + h1);
       }
     }
     if (lane < NV) {

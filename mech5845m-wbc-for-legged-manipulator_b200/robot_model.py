@@ -625,7 +625,7 @@ class RobotModel:
             self.current_joint_config = q_next
         return self.qdot
 
-    def step_host(self, host_in, host_out, chunks=8):
+    def step_host(self, host_in, host_out, chunks=8, resident_state=False):
         """The fused tick with HOST buffers (what a caller holding NumPy arrays pays end to end).
 
         ``host_in``: dict of pinned float64 CPU tensors q [N, nq], targets [N, 18], mem [N, 72], ref [N, 24];
@@ -633,6 +633,10 @@ class RobotModel:
         The batch is cut into ``chunks`` contiguous slices that go host -> device, through the fused kernel and back
         on three side streams, so the PCIe copies of one slice overlap the kernel of another; the current stream
         waits for all of them.  Returns (h2d_bytes, d2h_bytes).
+
+        ``resident_state``: only the per-tick inputs (q, targets) travel; the task memory and the per-robot references
+        stay where the reference keeps them -- in the controller object (``prev_EE_pos`` ... ``initial_trunk_pos``,
+        Robot_Wrapper4.py:133-140, 363-383), i.e. on the device.
         """
         N = self.N
         cfg = self._config()
@@ -642,6 +646,7 @@ class RobotModel:
         chunks = max(1, min(int(chunks), N))
         bounds = [(N * c) // chunks for c in range(chunks + 1)]
         dev_in = {"q": self.current_joint_config, "targets": self._targets, "mem": self._mem, "ref": self._ref}
+        moved = ("q", "targets") if resident_state else ("q", "targets", "mem", "ref")
         dev_out = {"qdot": self.qdot, "status": self.last_status, "iters": self.last_iters}
         start = torch.cuda.Event()
         start.record(cur)
@@ -654,7 +659,7 @@ class RobotModel:
                 st = self._side_streams[c % len(self._side_streams)]
                 st.wait_event(start)
                 with torch.cuda.stream(st):
-                    for k in dev_in:
+                    for k in moved:
                         dev_in[k][lo:hi].copy_(host_in[k][lo:hi], non_blocking=True)
                     io = cabi.WbcStepIO()
                     io.q = dev_in["q"][lo:hi].data_ptr()
@@ -674,7 +679,7 @@ class RobotModel:
                     done.append(ev)
         for ev in done:
             cur.wait_event(ev)
-        h2d = sum(host_in[k].numel() * 8 for k in ("q", "targets", "mem", "ref"))
+        h2d = sum(host_in[k].numel() * 8 for k in moved)
         d2h = host_out["qdot"].numel() * 8 + host_out["status"].numel() * 4 + host_out["iters"].numel() * 4
         return h2d, d2h
 
