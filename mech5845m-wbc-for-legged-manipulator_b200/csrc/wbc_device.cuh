@@ -284,6 +284,17 @@ __device__ __forceinline__ void scipy_quat_from_euler_xyz(const double* e, doubl
   quat_compose(qz, t, q);
 }
 
+// the same from the half-angle sines / cosines (computed one angle per lane by the caller)
+__device__ __forceinline__ void scipy_quat_from_half_sincos(double s0, double c0, double s1, double c1, double s2, double c2,
+                                                            double* q) {
+  const double qx[4] = {s0, 0.0, 0.0, c0};
+  const double qy[4] = {0.0, s1, 0.0, c1};
+  const double qz[4] = {0.0, 0.0, s2, c2};
+  double t[4];
+  quat_compose(qy, qx, t);
+  quat_compose(qz, t, q);
+}
+
 // Rotation.as_matrix()
 __device__ __forceinline__ void scipy_matrix_from_quat(const double* q, double* R) {
   const double x = q[0], y = q[1], z = q[2], w = q[3];
@@ -318,6 +329,35 @@ __device__ __forceinline__ void scipy_euler_xyz_from_quat(const double* q, doubl
   }
   a1 -= pi / 2;
   e[0] = wrap_pi(a0); e[1] = wrap_pi(a1); e[2] = wrap_pi(a2);
+}
+
+// The same conversion for ONE quaternion held by every lane of the warp (uniform input), with the transcendental calls
+// spread over lanes: one hypot, one atan2 and one fmod are executed warp-wide instead of 2 + 3 + 3 by a single lane.
+// Same functions on the same arguments, so the result is bit-identical to scipy_euler_xyz_from_quat.  All 32 lanes call;
+// every lane returns the full triple.
+__device__ __forceinline__ void warp_scipy_euler_xyz_from_quat(const double* q, int lane, double* e) {
+  const double pi = 3.141592653589793;
+  const double a = q[3] - q[1], b = q[0] + q[2], c = q[1] + q[3], d = q[2] - q[0];
+  const int r = lane % 3;
+  const double h = hypot((lane & 1) ? a : c, (lane & 1) ? b : d);   // lane 0: hypot(c, d), lane 1: hypot(a, b)
+  const double hcd = __shfl_sync(WBC_FULL_MASK, h, 0), hab = __shfl_sync(WBC_FULL_MASK, h, 1);
+  const double ty = (r == 0) ? b : ((r == 1) ? d : hcd);
+  const double tx = (r == 0) ? a : ((r == 1) ? c : hab);
+  const double t = atan2(ty, tx);
+  const double half_sum = __shfl_sync(WBC_FULL_MASK, t, 0), half_diff = __shfl_sync(WBC_FULL_MASK, t, 1);
+  double a1 = 2 * __shfl_sync(WBC_FULL_MASK, t, 2);
+  const bool case1 = fabs(a1) <= 1e-7, case2 = fabs(a1 - pi) <= 1e-7;
+  double a0, a2;
+  if (!(case1 || case2)) {
+    a0 = half_sum - half_diff;
+    a2 = half_sum + half_diff;
+  } else {
+    a2 = 0.0;
+    a0 = case1 ? 2 * half_sum : -2 * half_diff;
+  }
+  a1 -= pi / 2;
+  const double w = wrap_pi((r == 0) ? a0 : ((r == 1) ? a1 : a2));
+  e[0] = __shfl_sync(WBC_FULL_MASK, w, 0); e[1] = __shfl_sync(WBC_FULL_MASK, w, 1); e[2] = __shfl_sync(WBC_FULL_MASK, w, 2);
 }
 
 // ------------------------------------------------------------------------------------------------

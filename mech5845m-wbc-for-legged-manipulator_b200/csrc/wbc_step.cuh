@@ -593,13 +593,24 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     // quaternion-error term.
     sts_f64(clb_a + 8 * lane, 0.0);
     sts_f64(cub_a + 8 * lane, 0.0);
+    // Rotation.from_euler('xyz', default_ori) of the six targets needs 18 half-angle sincos: one per lane (lane 3 t + k:
+    // target t, angle k), gathered by lane t (the default Euler triples are contiguous in `ref`)
+    double hs0, hc0, hs1, hc1, hs2, hc2;
+    {
+      double hs, hc;
+      sincos(lds_f64(ref_a + 8 * (REF_DEF_EE_ORI + (lane < 18 ? lane : 0))) / 2.0, &hs, &hc);
+      const int t3 = 3 * (lane < 6 ? lane : 0);
+      hs0 = __shfl_sync(WBC_FULL_MASK, hs, t3);     hc0 = __shfl_sync(WBC_FULL_MASK, hc, t3);
+      hs1 = __shfl_sync(WBC_FULL_MASK, hs, t3 + 1); hc1 = __shfl_sync(WBC_FULL_MASK, hc, t3 + 1);
+      hs2 = __shfl_sync(WBC_FULL_MASK, hs, t3 + 2); hc2 = __shfl_sync(WBC_FULL_MASK, hc, t3 + 2);
+    }
+    double fkq[4] = {0, 0, 0, 1};
     __syncwarp();
     if (lane < 6) {
       const bool on = (cfg.task_mask >> lane) & 1;
       const bool is_trunk = lane == 5;
       const uint32_t T_a = omf_a + 8 * WBC_T_STRIDE * lane;
       double b6[6] = {0, 0, 0, 0, 0, 0};
-      double fkq[4] = {0, 0, 0, 1};
       if (is_trunk) {
         double Rf[9];
         lds_mat3(T_a, Rf);
@@ -608,11 +619,10 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       if (on) {
         const uint32_t prev_a = mem_a + 8 * (is_trunk ? MEM_PREV_TRUNK_REF : MEM_PREV_EE_POS + 3 * lane);
         const uint32_t prevR_a = mem_a + 8 * (is_trunk ? MEM_OLD_TRUNK_ROT : MEM_PREV_EE_ROT + 9 * lane);
-        double target[3], prev[3], fk[3], ref_vel[3], err[3], ge[3], eul[3];
+        double target[3], prev[3], fk[3], ref_vel[3], err[3], ge[3];
         lds_vec3(tg_a + 24 * lane, target);
         lds_vec3(prev_a, prev);
         lds_vec3(T_a + 72, fk);
-        lds_vec3(ref_a + 8 * (REF_DEF_EE_ORI + 3 * lane), eul);        // default_trunk_ori follows the five EE entries
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           ref_vel[k] = (target[k] - prev[k]) * inv_dt;
@@ -621,7 +631,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
         const double* G = is_trunk ? cfg.trunk_gain_pos : cfg.ee_gain_pos[lane < 5 ? lane : 0];
         mat3_vec(G, err, ge);
         double qref[4], Rref[9], prevR[9], dR[9], X[9], sk[9];
-        scipy_quat_from_euler_xyz(eul, qref);
+        scipy_quat_from_half_sincos(hs0, hc0, hs1, hc1, hs2, hc2, qref);
         scipy_matrix_from_quat(qref, Rref);
         lds_mat3(prevR_a, prevR);
 #pragma unroll
@@ -651,16 +661,20 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       }
 #pragma unroll
       for (int r = 0; r < 6; ++r) sts_f64(bs_a + 8 * (6 * lane + r), b6[r]);
-      if (is_trunk && row_trunk >= 0) {                                  // trunkConstraint (:707-754)
-        double eul[3], ip[3], ie[3];
-        scipy_euler_xyz_from_quat(fkq, eul);
-        lds_vec3(ref_a + 8 * REF_INIT_TRUNK_POS, ip);
-        lds_vec3(ref_a + 8 * REF_INIT_TRUNK_EUL, ie);
-        const double cur[4] = {lds_f64(T_a + 88), eul[0], eul[1], eul[2]};
-        const double z_var = ip[2] * 0.25;
-        const double var = 1.5 * 0.1;
-        const double lo[4] = {ip[2] - z_var, ie[0] - var, ie[1] - var, ie[2] - var};
-        const double up[4] = {ip[2] + z_var, ie[0] + var, ie[1] + var, ie[2] + var};
+    }
+    if (row_trunk >= 0) {                                              // trunkConstraint (:707-754), warp level
+      double fq[4], eul[3], ip[3], ie[3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fq[k] = __shfl_sync(WBC_FULL_MASK, fkq[k], WBC_FRAME_TRUNK);
+      warp_scipy_euler_xyz_from_quat(fq, lane, eul);
+      lds_vec3(ref_a + 8 * REF_INIT_TRUNK_POS, ip);
+      lds_vec3(ref_a + 8 * REF_INIT_TRUNK_EUL, ie);
+      const double cur[4] = {lds_f64(omf_a + 8 * (WBC_T_STRIDE * WBC_FRAME_TRUNK) + 88), eul[0], eul[1], eul[2]};
+      const double z_var = ip[2] * 0.25;
+      const double var = 1.5 * 0.1;
+      const double lo[4] = {ip[2] - z_var, ie[0] - var, ie[1] - var, ie[2] - var};
+      const double up[4] = {ip[2] + z_var, ie[0] + var, ie[1] + var, ie[2] + var};
+      if (lane == 0) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           sts_f64(clb_a + 8 * (row_trunk + r), ((lo[r] - cur[r]) * inv_dt) * 0.5);
