@@ -1,5 +1,6 @@
 // wbc_kernels.cu -- kernels + C ABI of libwbc_b200.so (see include/wbc_b200.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -58,7 +59,7 @@ template <bool SPLIT> struct StepWarps {
 #else
 #define WBC_STEP_BOUNDS(SPLIT) __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>::ctas)
 #endif
-template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF>
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF, bool RED>
 __global__ void WBC_STEP_BOUNDS(SPLIT) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
@@ -66,7 +67,7 @@ __global__ void WBC_STEP_BOUNDS(SPLIT) wbc_step_kernel(const __grid_constant__ S
   constexpr StepLayout L = step_layout(NV);
   const int warp = threadIdx.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
-  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF>(P, Ms, ws);
+  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF, RED>(P, Ms, ws);
 }
 
 // FK + frame Jacobians accessor (HBM-write bound): one state per warp
@@ -511,7 +512,7 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
 
 static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15); }
 
-template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0>
+template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0, bool RED = false>
 static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
   constexpr StepLayout L = step_layout(NV);
   const size_t per_warp = (size_t)L.total * sizeof(double);
@@ -522,7 +523,7 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
   if (warps > StepWarps<SPLIT>::value) warps = StepWarps<SPLIT>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
   const size_t smem = model_smem_bytes() + warps * per_warp;
-  auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD, NF>;
+  auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD, NF, RED>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + warps - 1) / warps;
   int grid = (int)(need < (long long)model->sm_count * ctas ? need : (long long)model->sm_count * ctas);
@@ -548,8 +549,12 @@ static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_
   if (P.nC <= 16) {
     // velDamperJointConstraints locks v >= gripper_joint_id - 2 + 6 (lb = ub = 0, :627-631): when these are exactly the
     // last three DoFs (both arms) the solver eliminates them at compile time
-    if (NV - (P.cfg.gripper_joint_id - 2 + 6) == 3)
+    if (NV - (P.cfg.gripper_joint_id - 2 + 6) == 3) {
+      // the twelve foot equality rows eliminated up front (wbc_qp_red.inc) when model and configuration allow it
+      if constexpr (!DBG)
+        if (P.red_ok && !fd) return launch_step_k<NV, DBG, true, false, 3, true>(model, P, st, info);
       return fd ? launch_step_k<NV, DBG, true, true, 3>(model, P, st, info) : launch_step_k<NV, DBG, true, false, 3>(model, P, st, info);
+    }
     return fd ? launch_step_k<NV, DBG, true, true>(model, P, st, info) : launch_step_k<NV, DBG, true, false>(model, P, st, info);
   }
   return fd ? launch_step_k<NV, DBG, false, true>(model, P, st, info) : launch_step_k<NV, DBG, false, false>(model, P, st, info);
@@ -562,6 +567,38 @@ static int launch_step(const WbcModel* model, const StepParams& P, cudaStream_t 
     case 26: return launch_step_t<26, DBG>(model, P, st, info);
     default: return fail(WBC_ERR_UNSUPPORTED, "the fused step kernel is instantiated for nv = 25 (A1 + PX100) and nv = 26 (A1 + WX200)%s");
   }
+}
+
+// Can the QP start from the reduced (null-space) front of wbc_qp_red.inc?  Needs: the four foot constraints on and the
+// gripper's off (its rows would be three more equalities), at most 16 rows, every foot frame supported by the six
+// free-flyer columns plus three consecutive limb columns [6 + 3 j, 9 + 3 j) (each j once), and no other row of C
+// touching a leg column (so that C Z is a column selection).  WBC_B200_NO_REDUCED=1 switches it off (A/B runs).
+static void set_reduced(const DevModel& M, StepParams* P) {
+  P->red_ok = 0;
+  P->red_rows = 0;
+  P->red_feet_mask = 0;
+  const char* off = getenv("WBC_B200_NO_REDUCED");
+  if (off && off[0] == '1') return;
+  if (P->nC > 16 || P->row_com >= 0 || P->row_ee[4] >= 0) return;
+  unsigned seen = 0;
+  for (int t = 0; t < 4; ++t) {
+    if (P->row_ee[t] < 0) return;
+    const unsigned supp = (unsigned)M.frame_supp[t];
+    if ((supp & 0x3Fu) != 0x3Fu) return;
+    const unsigned limb = supp >> 6;
+    int j = -1;
+    for (int b = 0; b < 4; ++b)
+      if (limb == (7u << (3 * b))) j = b;
+    if (j < 0 || ((seen >> j) & 1u)) return;
+    seen |= 1u << j;
+    P->red_rows |= (unsigned)P->row_ee[t] << (8 * j);
+    P->red_feet_mask |= 7u << P->row_ee[t];
+  }
+  const unsigned legs = 0xFFFu << 6;
+  if (P->row_trunk >= 0 && ((unsigned)M.frame_supp[WBC_FRAME_TRUNK] & legs)) return;
+  for (int e = 0; e < P->cfg.n_extra_rows; ++e)
+    if ((unsigned)M.frame_supp[P->cfg.extra_frame[e]] & legs) return;
+  P->red_ok = 1;
 }
 
 static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, StepParams* P) {
@@ -591,6 +628,7 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
     if (ident) P->flags |= WBC_STEP_FLAG_WEIGHTS_IDENTITY;   // W = I: W (J w) == J w exactly, skip the 6x6 products
   }
   if (P->nC > WBC_MAX_NC) return fail(WBC_ERR_UNSUPPORTED, "more than 32 constraint rows%s");
+  set_reduced(model->host, P);
   return WBC_OK;
 }
 

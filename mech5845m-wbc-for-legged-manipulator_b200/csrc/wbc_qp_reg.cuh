@@ -43,6 +43,9 @@ struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byt
   uint32_t C;        // [nC][LD] constraint rows (read once; up to two doubles past the end are touched)
   uint32_t clb, cub; // [32] each: row bounds (input)
   uint32_t dd;       // [64]: |d|^2 of the box constraints [0, 32) and of the rows [32, 64)
+  // reduced (null-space) front, RED instantiation only: first row of C of the foot whose limb columns are
+  // [6 + 3 j, 9 + 3 j), one byte per j; bit mask of the twelve foot rows
+  uint32_t red_rows, feet_mask;
 };
 
 // 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free
@@ -88,7 +91,7 @@ __device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
 #ifndef WBC_QP_KEQ
 #define WBC_QP_KEQ 12      // equality rows with a dedicated straight-line block each (static position in the working set)
 #endif
-template <int NV, bool SPLIT, bool SYNC = false, int NF = 0>
+template <int NV, bool SPLIT, bool SYNC = false, int NF = 0, bool RED = false>
 __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
                                                       const int nC, double g, const double lb_in, const double ub_in,
                                                       const int max_iter, double& x_out) {
@@ -121,6 +124,18 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   for (int o = 16; o > 0; o >>= 1) hd = fmax(hd, __shfl_xor_sync(WBC_FULL_MASK, hd, o));
   const double piv_min = WBC_QP_PIVOT_REL * fmax(hd, 0.0);
 
+  // state handed from the front (factorisation + equality rows) to the inequality loop
+  double Jr[NQ], Dr[ND];
+  const uint32_t lo_a = rk_a, up_a = rk_a + 8 * 32;     // per-lane bounds (once 1 / L_kk is dead)
+  double x = 0.0, ax = 0.0;
+  int iq = 0, p_eq = 0;
+  int ws_c = -1, slot = lane;                // per working-set position (lane = position)
+  double u = 0.0, rinv = 0.0;
+  int bstat = 0, cstat = 0;                  // 0 none 1 lower 2 upper 3 eq
+  bool fixed = false;
+  bool use_red = false;
+#include "wbc_qp_red.inc"
+  if (!use_red) {
   if (NF > 0) {                              // g_i += sum_k H[i][k] x_k over the statically fixed variables
 #pragma unroll
     for (int k = NQ; k < NV; ++k) {
@@ -132,7 +147,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   // Per-lane bounds live in shared memory during the iterations (lo[0..32) | up[32..64) in `col` once the
   // factorisation is done; row bounds in S.clb / S.cub): registers are the scarce resource of this kernel.
   const unsigned eqb = __ballot_sync(WBC_FULL_MASK, act && lb_in == ub_in);
-  const bool fixed = (eqb >> lane) & 1u;
+  fixed = (eqb >> lane) & 1u;
   if (eqb) {
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
@@ -178,7 +193,6 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   // ---- phase B: forward substitutions L^-1 [I | g | C^T], column-oriented, all right-hand sides at once:
   //      lane i < NQ: e_i (-> row i of J = L^-T), lane NQ: g, second array: the rows of C with the fixed
   //      variables' coefficients moved into `shift`
-  double Jr[NQ], Dr[ND];
   double shift = 0.0;                                   // sum_k C[c][k] x_k over the fixed variables
   {
     const uint32_t crow_a = S.C + 8 * ((has_row ? crow : 0) * LD) + doff;
@@ -257,8 +271,6 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
 
   if (SYNC) phase_sync<true>();
   // ---- |d|^2 of every constraint (invariant under the orthogonal updates), x0 = -J (L^-1 g), C x0 -----
-  const uint32_t lo_a = rk_a, up_a = rk_a + 8 * 32;     // 1 / L_kk is dead now
-  double x, ax;
   {
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
@@ -301,10 +313,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   }
 
   // ---- working set ----------------------------------------------------------------------------------
-  int iq = 0, p_eq = 0;
-  int ws_c = -1, slot = lane;                // per working-set position (lane = position)
-  double u = 0.0, rinv = 0.0;
-  int bstat = (fixed || sfix) ? 3 : 0, cstat = 0;      // 0 none 1 lower 2 upper 3 eq
+  bstat = (fixed || sfix) ? 3 : 0;
   unsigned eq_mask_row = __ballot_sync(WBC_FULL_MASK, lane < nC && lds_f64(S.clb + 8 * lane) == lds_f64(S.cub + 8 * lane));
 
   // ---- equality rows first, in index order: no step-length logic, no multipliers, no column of R, no d1 ----
@@ -502,6 +511,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     p_eq = iq;
     __syncwarp();
   }
+  }   // !use_red
 
   // One flat loop: every pass is one step of the method for the current candidate (pick one if there is none).
   // (inequalities only: the equalities are in the working set by now, so is_eq is a compile-time false here)

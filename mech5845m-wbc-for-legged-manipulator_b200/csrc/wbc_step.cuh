@@ -69,6 +69,10 @@ struct StepParams {
   long long N;
   int nC, m_rows, flags;
   int row_com, row_trunk, row_ee[5], row_extra;   // first row of each constraint block in C (-1: off), set_rows()
+  // reduced (null-space) QP front (wbc_qp_red.inc): usable for this model + configuration, first C row of the foot
+  // owning limb columns [6 + 3 j, 9 + 3 j) (one byte per j), bit mask of the foot rows; set_reduced()
+  int red_ok;
+  unsigned red_rows, red_feet_mask;
 };
 
 // Row layout of C implied by the constraint mask (findConstraints order, Robot_Wrapper4.py:764-836): computed once on
@@ -493,7 +497,7 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 // one fetch feeds all warps.  Padding warps shadow the last state (no writes) so the barriers stay uniform.
 // Shared memory is addressed through 32-bit shared-window addresses (wbc_device.cuh: smem_addr, lds_*, sts_*).
 // NF: the last NF velocity DoFs are locked by the configuration (gripper + fingers, lb = ub = 0): the QP runs on NV - NF variables
-template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0>
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0, bool RED = false>
 __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws) {
   constexpr StepLayout L = step_layout(NV);
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
@@ -932,14 +936,20 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     QpResult res;
     {
       double h[NV];
+      if (RED) {                       // lane NV - NF rides along with g^T as its "row of H" (the locked DoF's row is unused)
+        sts_f64_if(lane < NV - NF, hs_a + 8 * (LD * (NV - NF) + lane), gk);
+        __syncwarp();
+      }
 #pragma unroll
-      for (int l = 0; l < NV; ++l) h[l] = (lane < NV - NF) ? lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0) : 0.0;
+      for (int l = 0; l < NV; ++l)
+        h[l] = (lane < NV - NF + (RED ? 1 : 0)) ? lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0) : 0.0;
       const double hdiag = (lane < NV) ? lds_f64(hrow_a + 8 * lane) + aj * aj : 0.0;
       __syncwarp();                    // Hs becomes the solver's R factor
       QpRegShared S;
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
       S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
-      res = warp_qp_solve_reg<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
+      S.red_rows = P.red_rows; S.feet_mask = P.red_feet_mask;
+      res = warp_qp_solve_reg<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF, RED>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
     }
 
     phase_sync<PS>();            // (measured: dropping this barrier costs 6 %)
