@@ -88,6 +88,13 @@ __device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
 //       on NQ = NV - NF variables.  Contract: h[k] = H[lane][k] for lane < NQ and 0 for lane >= NQ; lb_in == ub_in
 //       on lanes [NQ, NV).  They are reported like the run-time fixed variables (equality-active, one working-set
 //       change each).
+// Out-of-line copy of the general solver: the per-state fallback of the reduced front (wbc_qp_red.inc).  Kept behind a
+// call so that the two fronts do not share one register allocation (inlined side by side they spill).
+template <int NV, bool SPLIT, int NF>
+__device__ __noinline__ QpResult warp_qp_solve_reg_cold(const QpRegShared S, const double* h_in, const double hdiag,
+                                                        const int nC, const double g, const double lb_in,
+                                                        const double ub_in, const int max_iter, double* x_out);
+
 #ifndef WBC_QP_KEQ
 #define WBC_QP_KEQ 12      // equality rows with a dedicated straight-line block each (static position in the working set)
 #endif
@@ -133,9 +140,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   double u = 0.0, rinv = 0.0;
   int bstat = 0, cstat = 0;                  // 0 none 1 lower 2 upper 3 eq
   bool fixed = false;
-  bool use_red = false;
 #include "wbc_qp_red.inc"
-  if (!use_red) {
+  if (!RED) {
   if (NF > 0) {                              // g_i += sum_k H[i][k] x_k over the statically fixed variables
 #pragma unroll
     for (int k = NQ; k < NV; ++k) {
@@ -511,7 +517,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
     p_eq = iq;
     __syncwarp();
   }
-  }   // !use_red
+  }   // !RED
 
   // One flat loop: every pass is one step of the method for the current candidate (pick one if there is none).
   // (inequalities only: the equalities are in the working set by now, so is_eq is a compile-time false here)
@@ -766,5 +772,18 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
 
   x_out = (fixed || sfix) ? lds_f64(lo_a + 8 * lane) : x;
   pack_active_sets(lane, NQ + NF, nC, bstat, cstat, res);
+  return res;
+}
+
+template <int NV, bool SPLIT, int NF>
+__device__ __noinline__ QpResult warp_qp_solve_reg_cold(const QpRegShared S, const double* h_in, const double hdiag,
+                                                        const int nC, const double g, const double lb_in,
+                                                        const double ub_in, const int max_iter, double* x_out) {
+  double h[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) h[k] = h_in[k];
+  double x;
+  const QpResult res = warp_qp_solve_reg<NV, SPLIT, false, NF, false>(S, h, hdiag, nC, g, lb_in, ub_in, max_iter, x);
+  *x_out = x;
   return res;
 }

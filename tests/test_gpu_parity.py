@@ -298,6 +298,41 @@ def test_config3_extension_rows_full_size():
     assert same_path.mean() > 0.97 and same_set.mean() > 0.90      # measured on B200: 0.992 / 0.950 (degenerate vertices)
 
 
+@pytest.mark.parametrize("name", ["a1_wx200", "a1_px100_pin_ver"])
+@pytest.mark.parametrize("kind", ["ineq_rows", "eq_row_fallback", "general_front"])
+def test_reduced_front_against_c_oracle_and_general_front(name, kind, monkeypatch):
+    """The null-space front of the QP (csrc/wbc_qp_red.inc: foot rows eliminated up front) against the C oracle, which
+    enters the twelve rows one by one: same minimiser, same iteration count, same active set.  `ineq_rows`: feet + two
+    extra inequality rows on the trunk frame (rows without leg support ride along as column selections);
+    `eq_row_fallback`: one extra row with lo == hi makes the equality set differ from the foot rows, so every state
+    takes the in-kernel fallback to the general front; `general_front`: the same problem with the reduced front
+    switched off (WBC_B200_NO_REDUCED=1), i.e. the A/B baseline."""
+    import wbc_b200
+    from oracle import c_port
+    if kind == "general_front":
+        monkeypatch.setenv("WBC_B200_NO_REDUCED", "1")
+    N = 2048
+    robot = _robot(name, N, P1_TASKS, dict(CoM=False, Trunk=False, FR=True, FL=True, RR=True, RL=True, Grip=False), True)
+    rf = wbc_b200._cabi.RF_LOCAL_WORLD_ALIGNED
+    if kind == "eq_row_fallback":
+        robot.extra_rows = [(5, rf, [0, 0, 1, 0, 0, 0], 0.01, 0.01), (5, rf, [0, 0, 0, 0, 0, 1], -0.2, 0.2)]
+    else:
+        robot.extra_rows = [(5, rf, [0, 0, 1, 0, 0, 0], -0.05, 0.05), (5, rf, [0, 0, 0, 0, 0, 1], -0.2, 0.2)]
+    q, targets = _load(robot, N, 20260007, 5e-3)
+    mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=False)
+    assert (robot.last_status == 0).all()
+    ts, table = c_port.table_struct(name)
+    ref = c_port.step(ts, c_port.config_struct(robot, table), q, targets.cpu().numpy(), mem0.cpu().numpy(),
+                      ref0.cpu().numpy(), robot.dt)
+    assert (ref["status"] == 0).all()
+    assert np.abs(x.cpu().numpy() - ref["qdot"]).max() < QP_TOL
+    same_path = robot.last_iters.cpu().numpy() == ref["iters"]
+    same_set = (robot.last_active_set.cpu().numpy().astype(np.uint64) == ref["active_set"]).all(axis=1)
+    assert float((robot.last_active_set[:, 1] & 0xF000000).ne(0).double().mean()) > 0.05     # the extra rows do bind
+    assert same_path.mean() > 0.995 and same_set.mean() > 0.995, (same_path.mean(), same_set.mean())
+
+
 def test_bootstrap_matches_oracle():
     """f4: the constructor bootstrap (setInitialState, Robot_Wrapper4.py:196-351) batched -- 60 of its 2000 ticks
     (linear EE trajectories, bounds-only QP, plain integrate) and the final re-basing, against the oracle."""
