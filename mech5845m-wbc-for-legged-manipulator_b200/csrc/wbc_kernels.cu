@@ -577,6 +577,7 @@ static void set_reduced(const DevModel& M, StepParams* P) {
   P->red_ok = 0;
   P->red_rows = 0;
   P->red_feet_mask = 0;
+  P->red_blk = 0;
   const char* off = getenv("WBC_B200_NO_REDUCED");
   if (off && off[0] == '1') return;
   if (P->nC > 16 || P->row_com >= 0 || P->row_ee[4] >= 0) return;
@@ -592,6 +593,7 @@ static void set_reduced(const DevModel& M, StepParams* P) {
     if (j < 0 || ((seen >> j) & 1u)) return;
     seen |= 1u << j;
     P->red_rows |= (unsigned)P->row_ee[t] << (8 * j);
+    P->red_blk |= (unsigned)j << (2 * t);
     P->red_feet_mask |= 7u << P->row_ee[t];
   }
   const unsigned legs = 0xFFFu << 6;

@@ -36,6 +36,8 @@
 #pragma once
 #include "wbc_qp.cuh"
 
+#define WBC_LDT 38    // doubles per column of the transposed task rows: 304 B = 19 x 16 B, conflict-free 128-bit accesses
+
 struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byte aligned
   uint32_t R;        // [NV][NV + 2]: columns of L during the factorisation, then R with LD = NV | 1
   uint32_t col;      // [64]: 1 / L_kk
@@ -46,6 +48,9 @@ struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byt
   // reduced (null-space) front, RED instantiation only: first row of C of the foot whose limb columns are
   // [6 + 3 j, 9 + 3 j), one byte per j; bit mask of the twelve foot rows
   uint32_t red_rows, feet_mask;
+  uint32_t red_blk;  // 2 bits per foot task t: j of its limb columns [6 + 3 j, 9 + 3 j)
+  uint32_t b;        // [36] targets of the Cartesian task rows
+  uint32_t gs;       // [NQ - 11][WBC_LDT] scratch: columns of the reduced task rows
 };
 
 // 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free
@@ -91,17 +96,20 @@ __device__ __forceinline__ void publish_row(uint32_t a0, const double (&a)[N]) {
 // Out-of-line copy of the general solver: the per-state fallback of the reduced front (wbc_qp_red.inc).  Kept behind a
 // call so that the two fronts do not share one register allocation (inlined side by side they spill).
 template <int NV, bool SPLIT, int NF>
-__device__ __noinline__ QpResult warp_qp_solve_reg_cold(const QpRegShared S, const double* h_in, const double hdiag,
-                                                        const int nC, const double g, const double lb_in,
+__device__ __noinline__ QpResult warp_qp_solve_reg_cold(const QpRegShared S, const double* a_in, const double aj,
+                                                        const double bj, const int nC, const double lb_in,
                                                         const double ub_in, const int max_iter, double* x_out);
 
 #ifndef WBC_QP_KEQ
 #define WBC_QP_KEQ 12      // equality rows with a dedicated straight-line block each (static position in the working set)
 #endif
-template <int NV, bool SPLIT, bool SYNC = false, int NF = 0, bool RED = false>
-__device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
-                                                      const int nC, double g, const double lb_in, const double ub_in,
-                                                      const int max_iter, double& x_out) {
+// RED: the reduced front of wbc_qp_red.inc; h / hdiag / g are not read then, the problem arrives as the task-row columns
+// `ta` (lane l: column l of the 36 weighted Cartesian rows), S.b and the joint task (aj, bj).
+template <int NV, bool SPLIT, bool SYNC, int NF, bool RED>
+__device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, double (&h)[NV], const double hdiag,
+                                                           const int nC, double g, const double lb_in, const double ub_in,
+                                                           const int max_iter, double& x_out, const double (&ta)[36],
+                                                           const double aj, const double bj) {
   constexpr int NQ = NV - NF;                // variables of the factorisation
   constexpr int n = NQ;
   constexpr int LD = NV | 1;                 // leading dimension of C (caller's layout) and of R
@@ -127,9 +135,11 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   res.iters = NF;
 
   double hd = (lane < NV) ? hdiag : 0.0;
+  if (!RED) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) hd = fmax(hd, __shfl_xor_sync(WBC_FULL_MASK, hd, o));
-  const double piv_min = WBC_QP_PIVOT_REL * fmax(hd, 0.0);
+    for (int o = 16; o > 0; o >>= 1) hd = fmax(hd, __shfl_xor_sync(WBC_FULL_MASK, hd, o));
+  }
+  double piv_min = WBC_QP_PIVOT_REL * fmax(hd, 0.0);
 
   // state handed from the front (factorisation + equality rows) to the inequality loop
   double Jr[NQ], Dr[ND];
@@ -775,15 +785,59 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, doubl
   return res;
 }
 
+template <int NV, bool SPLIT, bool SYNC = false, int NF = 0>
+__device__ __forceinline__ QpResult warp_qp_solve_reg(const QpRegShared S, double (&h)[NV], const double hdiag,
+                                                      const int nC, double g, const double lb_in, const double ub_in,
+                                                      const int max_iter, double& x_out) {
+  const double ta[36] = {};
+  return warp_qp_solve_reg_impl<NV, SPLIT, SYNC, NF, false>(S, h, hdiag, nC, g, lb_in, ub_in, max_iter, x_out, ta, 0.0, 0.0);
+}
+
+// Fallback of the reduced front: H = A^T A + aj^2 I and g = -A^T b - aj b_joint assembled column by column from the
+// task-row columns (compact, not fast: this path runs for states that fail the preconditions of wbc_qp_red.inc), then
+// the general solver.
 template <int NV, bool SPLIT, int NF>
-__device__ __noinline__ QpResult warp_qp_solve_reg_cold(const QpRegShared S, const double* h_in, const double hdiag,
-                                                        const int nC, const double g, const double lb_in,
+__device__ __noinline__ QpResult warp_qp_solve_reg_cold(const QpRegShared S, const double* a_in, const double aj,
+                                                        const double bj, const int nC, const double lb_in,
                                                         const double ub_in, const int max_iter, double* x_out) {
-  double h[NV];
+  constexpr int NQ = NV - NF;
+  const int lane = threadIdx.x & 31;
+  double a[36];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) h[k] = h_in[k];
+  for (int r = 0; r < 36; ++r) a[r] = a_in[r];
+  double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+  for (int r = 0; r < 18; ++r) {
+    const double2 b2 = lds_f64x2(S.b + 16 * r);
+    g0 = fma(-a[2 * r], b2.x, g0);
+    g1 = fma(-a[2 * r + 1], b2.y, g1);
+  }
+  const double g = (g0 + g1) - aj * bj;
+  double h[NV];
+  double hdiag = 0.0;
+  const uint32_t buf = S.col;                // 64 doubles, free until the factorisation
+#pragma unroll
+  for (int l = 0; l < NV; ++l) {
+    if (lane == l) {
+#pragma unroll
+      for (int r = 0; r < 18; ++r) sts_f64x2(buf + 16 * r, a[2 * r], a[2 * r + 1]);
+    }
+    __syncwarp();
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 18; ++r) {
+      const double2 c2 = lds_f64x2(buf + 16 * r);
+      s0 = fma(a[2 * r], c2.x, s0);
+      s1 = fma(a[2 * r + 1], c2.y, s1);
+    }
+    const double hl = (s0 + s1) + ((l == lane) ? aj * aj : 0.0);
+    if (l == lane) hdiag = hl;
+    h[l] = (lane < NQ) ? hl : 0.0;
+    __syncwarp();
+  }
+  if (lane >= NV) hdiag = 0.0;
   double x;
-  const QpResult res = warp_qp_solve_reg<NV, SPLIT, false, NF, false>(S, h, hdiag, nC, g, lb_in, ub_in, max_iter, x);
+  const QpResult res = warp_qp_solve_reg<NV, SPLIT, false, NF>(S, h, hdiag, nC, g, lb_in, ub_in, max_iter, x);
   *x_out = x;
   return res;
 }

@@ -36,7 +36,6 @@ struct StepLayout {   // per-warp shared-memory layout in doubles (every offset 
 };
 
 __host__ __device__ inline int wbc_ld(int nv) { return nv | 1; }
-#define WBC_LDT 38    // doubles per column of the transposed task rows: 304 B = 19 x 16 B, conflict-free 128-bit accesses
 
 // (sized for WBC_MAX_NC rows whatever the configuration: the layout is a compile-time constant of the kernel, so every
 //  shared-memory address of the tick is [per-warp base + immediate])
@@ -72,7 +71,7 @@ struct StepParams {
   // reduced (null-space) QP front (wbc_qp_red.inc): usable for this model + configuration, first C row of the foot
   // owning limb columns [6 + 3 j, 9 + 3 j) (one byte per j), bit mask of the foot rows; set_reduced()
   int red_ok;
-  unsigned red_rows, red_feet_mask;
+  unsigned red_rows, red_feet_mask, red_blk;
 };
 
 // Row layout of C implied by the constraint mask (findConstraints order, Robot_Wrapper4.py:764-836): computed once on
@@ -787,6 +786,8 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     // broadcast loads and six FMAs.  Pairs outside the frame's support are structural zeros and are skipped.
     __syncwarp();                      // all reads of oMi (aliased by Hs) and bs writes are done
     const uint32_t hrow_a = hs_a + 8 * LD * (lane < NV ? lane : 0);
+    double gk = 0.0;
+    if (!RED) {                        // (RED: the solver's front assembles the reduced Hessian from `a` itself)
     if (lane < NV) {
       const uint32_t da = ast_a + 8 * WBC_LDT * lane;
 #pragma unroll
@@ -795,7 +796,6 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       for (int l = 0; l < NV; ++l) sts_f64(hrow_a + 8 * l, 0.0);
     }
     __syncwarp();
-    double gk = 0.0;
     {
       double g0 = 0.0, g1 = 0.0;
 #pragma unroll
@@ -842,6 +842,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       for (int l = 0; l < 6; ++l) sts_f64(hrow_a + 8 * l, hb[l]);
     }
     __syncwarp();
+    }   // !RED
 
     if (DEBUG_OUT) {
       const WbcAssembleOut& D = P.dbg;
@@ -936,20 +937,18 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     QpResult res;
     {
       double h[NV];
-      if (RED) {                       // lane NV - NF rides along with g^T as its "row of H" (the locked DoF's row is unused)
-        sts_f64_if(lane < NV - NF, hs_a + 8 * (LD * (NV - NF) + lane), gk);
-        __syncwarp();
-      }
 #pragma unroll
       for (int l = 0; l < NV; ++l)
-        h[l] = (lane < NV - NF + (RED ? 1 : 0)) ? lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0) : 0.0;
-      const double hdiag = (lane < NV) ? lds_f64(hrow_a + 8 * lane) + aj * aj : 0.0;
+        h[l] = (!RED && lane < NV - NF) ? lds_f64(hrow_a + 8 * l) + ((l == lane) ? aj * aj : 0.0) : 0.0;
+      const double hdiag = (!RED && lane < NV) ? lds_f64(hrow_a + 8 * lane) + aj * aj : 0.0;
       __syncwarp();                    // Hs becomes the solver's R factor
       QpRegShared S;
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
       S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
-      S.red_rows = P.red_rows; S.feet_mask = P.red_feet_mask;
-      res = warp_qp_solve_reg<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF, RED>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter, x);
+      S.red_rows = P.red_rows; S.feet_mask = P.red_feet_mask; S.red_blk = P.red_blk;
+      S.b = bs_a; S.gs = ast_a + 8 * 448;           // (C takes at most 16 rows of LD doubles of this block)
+      res = warp_qp_solve_reg_impl<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF, RED>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter,
+                                                                                    x, a, aj, bj);
     }
 
     phase_sync<PS>();            // (measured: dropping this barrier costs 6 %)
