@@ -49,22 +49,25 @@ __device__ __forceinline__ void stage_model(const DevModel* __restrict__ g, DevM
 #ifndef WBC_STEP_CTAS
 #define WBC_STEP_CTAS 1       // CTAs per SM of the SPLIT kernel (WBC_STEP_WARPS warps each)
 #endif
-template <bool SPLIT> struct StepWarps {
-  static constexpr int value = SPLIT ? WBC_STEP_WARPS : 8;
+#ifndef WBC_STEP_WARPS_RED
+#define WBC_STEP_WARPS_RED 16 // the reduced-front instantiation: 128 registers, 13.5 KB of shared memory per warp
+#endif
+template <bool SPLIT, bool RED = false> struct StepWarps {
+  static constexpr int value = RED ? WBC_STEP_WARPS_RED : (SPLIT ? WBC_STEP_WARPS : 8);
   static constexpr int ctas = SPLIT ? WBC_STEP_CTAS : 1;
 };
 
 #ifdef WBC_STEP_MAXNREG       // A/B builds: explicit register cap instead of the launch-bounds heuristic
-#define WBC_STEP_BOUNDS(SPLIT) __maxnreg__(WBC_STEP_MAXNREG)
+#define WBC_STEP_BOUNDS(SPLIT, RED) __maxnreg__(WBC_STEP_MAXNREG)
 #else
-#define WBC_STEP_BOUNDS(SPLIT) __launch_bounds__(32 * StepWarps<SPLIT>::value, StepWarps<SPLIT>::ctas)
+#define WBC_STEP_BOUNDS(SPLIT, RED) __launch_bounds__(32 * StepWarps<SPLIT, RED>::value, StepWarps<SPLIT, RED>::ctas)
 #endif
 template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF, bool RED>
-__global__ void WBC_STEP_BOUNDS(SPLIT) wbc_step_kernel(const __grid_constant__ StepParams P) {
+__global__ void WBC_STEP_BOUNDS(SPLIT, RED) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
   stage_model(P.model, Ms);
-  constexpr StepLayout L = step_layout(NV);
+  constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
   const int warp = threadIdx.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
   warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF, RED>(P, Ms, ws);
@@ -514,13 +517,13 @@ static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15);
 
 template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0, bool RED = false>
 static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
-  constexpr StepLayout L = step_layout(NV);
+  constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
   const size_t per_warp = (size_t)L.total * sizeof(double);
   int max_optin = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, model->device));
-  constexpr int ctas = StepWarps<SPLIT>::ctas;
+  constexpr int ctas = StepWarps<SPLIT, RED>::ctas;
   int warps = (int)(((size_t)(max_optin + 1024) / ctas - 1024 - model_smem_bytes()) / per_warp);
-  if (warps > StepWarps<SPLIT>::value) warps = StepWarps<SPLIT>::value;
+  if (warps > StepWarps<SPLIT, RED>::value) warps = StepWarps<SPLIT, RED>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
   const size_t smem = model_smem_bytes() + warps * per_warp;
   auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD, NF, RED>;

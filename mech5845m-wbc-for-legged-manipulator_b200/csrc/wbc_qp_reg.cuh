@@ -50,7 +50,6 @@ struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byt
   uint32_t red_rows, feet_mask;
   uint32_t red_blk;  // 2 bits per foot task t: j of its limb columns [6 + 3 j, 9 + 3 j)
   uint32_t b;        // [36] targets of the Cartesian task rows
-  uint32_t gs;       // [NQ - 11][WBC_LDT] scratch: columns of the reduced task rows
 };
 
 // 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free

@@ -39,15 +39,20 @@ __host__ __device__ inline int wbc_ld(int nv) { return nv | 1; }
 
 // (sized for WBC_MAX_NC rows whatever the configuration: the layout is a compile-time constant of the kernel, so every
 //  shared-memory address of the tick is [per-warp base + immediate])
-__host__ __device__ constexpr StepLayout step_layout(int nv, int nC = WBC_MAX_NC) {
+// red: the instantiation with the reduced QP front (three locked DoFs, <= 16 rows): no H rows and no transposed task
+// rows; the first block holds the oMi scratch, then the front's scratch (576 doubles, wbc_qp_red.inc), then the R factor
+// of the inequality block -- or, for a state on the fallback path, the L columns / R factor of the general solver
+// ((nv - 3) rows of nv | 1 doubles + the 32-lane store overhang); the second block only the constraint rows.
+__host__ __device__ constexpr StepLayout step_layout(int nv, int nC = WBC_MAX_NC, bool red = false) {
   StepLayout L{};
   const int ld = nv | 1;
-  int r0 = nv * (nv + 2);                              // H rows, later the L columns / R factor of the QP ...
+  int r0 = red ? (nv - 3) * ld + 32 : nv * (nv + 2);   // H rows, later the L columns / R factor of the QP ...
   const int fk = WBC_MAX_JOINTS * WBC_T_STRIDE;        // ... aliased by the oMi scratch (dead before H is written)
   if (r0 < fk) r0 = fk;
+  if (red && r0 < 576) r0 = 576;
   r0 = (r0 + 1) & ~1;
-  int r1 = nv * WBC_LDT;                               // transposed task rows AsT, later the constraint rows C
-  if (r1 < nC * ld + 2) r1 = nC * ld + 2;
+  int r1 = red ? 16 * ld + 2 : nv * WBC_LDT;           // transposed task rows AsT, later the constraint rows C
+  if (!red && r1 < nC * ld + 2) r1 = nC * ld + 2;
   r1 = (r1 + 1) & ~1;
   L.hs = 0;
   L.ast = r0;
@@ -498,7 +503,7 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 // NF: the last NF velocity DoFs are locked by the configuration (gripper + fingers, lb = ub = 0): the QP runs on NV - NF variables
 template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0, bool RED = false>
 __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws) {
-  constexpr StepLayout L = step_layout(NV);
+  constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
   constexpr int LD = NV | 1;
   constexpr int nq = NV + 1;
@@ -946,7 +951,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
       S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
       S.red_rows = P.red_rows; S.feet_mask = P.red_feet_mask; S.red_blk = P.red_blk;
-      S.b = bs_a; S.gs = ast_a + 8 * 448;           // (C takes at most 16 rows of LD doubles of this block)
+      S.b = bs_a;
       res = warp_qp_solve_reg_impl<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF, RED>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter,
                                                                                     x, a, aj, bj);
     }
