@@ -783,9 +783,13 @@ int wbc_step_launch_info(const WbcModel* model, int32_t* grid, int32_t* block, i
   if (!model) return fail(WBC_ERR_INVALID_ARG, "null model%s");
   StepParams P;
   memset(&P, 0, sizeof(P));
-  P.nC = 16;
   P.N = 1 << 20;
   P.cfg.gripper_joint_id = model->host.nv - 7;   // the shipped arms: gripper + two fingers locked (the NF = 3 instantiation)
+  // the usual constraint set (sim3.py:145-148, BASELINE P2 / P3): trunk box + four feet -> the reduced-front instantiation
+  P.cfg.constraint_mask = WBC_CON_TRUNK | (WBC_CON_FR << 0) | (WBC_CON_FR << 1) | (WBC_CON_FR << 2) | (WBC_CON_FR << 3);
+  P.nC = cfg_nc(P.cfg);
+  set_rows(&P);
+  set_reduced(model->host, &P);
   int info[4] = {0, 0, 0, 0};
   int rc = launch_step<false>(model, P, nullptr, info);
   if (rc != WBC_OK) return rc;

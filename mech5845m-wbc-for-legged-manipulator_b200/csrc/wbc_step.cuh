@@ -562,6 +562,9 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
 #pragma unroll
     for (int t = 0; t < 6; ++t) supp[t] = (uint32_t)lds_s32(M_a + WBC_MOFF(frame_supp) + 4 * t);
     double a[36];
+    // (computed here only in the finite-difference modes, whose perturbed state must not reach A; otherwise after the
+    //  targets and bounds, right before its consumers: 72 registers less across the rotation chains)
+    auto task_rows = [&]() {
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
       const bool on = (cfg.task_mask >> t) & 1;
@@ -594,6 +597,8 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
         for (int r = 0; r < 6; ++r) a[6 * t + r] = 0.0;
       }
     }
+    };
+    if (FD) task_rows();
 
     // ---------------------------------------------------------------- targets b (lanes 0..5), constraint bounds
     // calcTargetVelEE3 (:1052-1157) on lanes 0..4 and calcTargetVelTrunk2 (:948-1015) on lane 5 share the
@@ -785,6 +790,44 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       bj = ((1.0 / NV) * lds_f64(q_a + 8 * ((lane < 6) ? lane : lane + 1))) * cfg.joint_task_weight;
     if (fd_on && lane < NV) bj = ((1.0 / NV) * u_fd) * cfg.joint_task_weight;
 
+    // ---------------------------------------------------------------- constraint rows
+    // (general instantiation: into the block of the transposed task rows once those are dead; reduced instantiation: that
+    //  block only ever holds C, so the rows are written before the task rows are computed -- shorter live range of `a`)
+    auto constraint_rows = [&]() {
+    if (lane < NV) {
+      const uint32_t c_a = ast_a + 8 * lane;
+      if (row_com >= 0) { sts_f64(c_a + 8 * LD * row_com, Jcom[0]); sts_f64(c_a + 8 * LD * (row_com + 1), Jcom[1]); }
+      if (row_trunk >= 0) {                                        // LWA rows z, wx, wy, wz of the trunk frame (:709)
+        double Jc[6], fp[3];
+        lds_vec3(omf_a + 8 * (WBC_T_STRIDE * WBC_FRAME_TRUNK + 9), fp);
+        frame_jac_lwa(Sc, (supp[WBC_FRAME_TRUNK] >> lane) & 1u, fp, false, Jc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sts_f64(c_a + 8 * LD * (row_trunk + r), Jc[2 + r]);
+      }
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        if (row_ee[i] >= 0) {                                      // WORLD linear rows (:758)
+          const bool sup = (supp[i] >> lane) & 1u;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) sts_f64(c_a + 8 * LD * (row_ee[i] + r), sup ? Sc[r] : 0.0);
+        }
+      }
+      for (int e = 0; e < cfg.n_extra_rows; ++e) {                 // extension rows (not in the reference)
+        const int f = cfg.extra_frame[e];
+        double T[12], Jc[6];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T[i] = lds_f64(omf_a + 8 * (WBC_T_STRIDE * f + i));
+        frame_jac_column(Sc, (uint32_t)lds_s32(M_a + WBC_MOFF(frame_supp) + 4 * f), lane, T, cfg.extra_rf[e], Jc);
+        double sacc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sacc += cfg.extra_coeff[e][c] * Jc[c];
+        sts_f64(c_a + 8 * LD * (row_extra + e), sacc);
+      }
+    }
+    };
+    if (RED) constraint_rows();
+    if (!FD) task_rows();
+
     // ---------------------------------------------------------------- H = A^T A, g = -A^T b
     // Column `lane` of the 36 Cartesian rows goes to shared memory transposed (AsT[lane][r]); then for every
     // (task t, supporting column l) pair lane i adds  sum_r A[6t+r][i] A[6t+r][l]  to H[i][l]: three 128-bit
@@ -879,37 +922,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       __syncwarp();
     }
 
-    // ---------------------------------------------------------------- constraint rows (AsT is dead now)
-    if (lane < NV) {
-      const uint32_t c_a = ast_a + 8 * lane;
-      if (row_com >= 0) { sts_f64(c_a + 8 * LD * row_com, Jcom[0]); sts_f64(c_a + 8 * LD * (row_com + 1), Jcom[1]); }
-      if (row_trunk >= 0) {                                        // LWA rows z, wx, wy, wz of the trunk frame (:709)
-        double Jc[6], fp[3];
-        lds_vec3(omf_a + 8 * (WBC_T_STRIDE * WBC_FRAME_TRUNK + 9), fp);
-        frame_jac_lwa(Sc, (supp[WBC_FRAME_TRUNK] >> lane) & 1u, fp, false, Jc);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) sts_f64(c_a + 8 * LD * (row_trunk + r), Jc[2 + r]);
-      }
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        if (row_ee[i] >= 0) {                                      // WORLD linear rows (:758)
-          const bool sup = (supp[i] >> lane) & 1u;
-#pragma unroll
-          for (int r = 0; r < 3; ++r) sts_f64(c_a + 8 * LD * (row_ee[i] + r), sup ? Sc[r] : 0.0);
-        }
-      }
-      for (int e = 0; e < cfg.n_extra_rows; ++e) {                 // extension rows (not in the reference)
-        const int f = cfg.extra_frame[e];
-        double T[12], Jc[6];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) T[i] = lds_f64(omf_a + 8 * (WBC_T_STRIDE * f + i));
-        frame_jac_column(Sc, (uint32_t)lds_s32(M_a + WBC_MOFF(frame_supp) + 4 * f), lane, T, cfg.extra_rf[e], Jc);
-        double sacc = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) sacc += cfg.extra_coeff[e][c] * Jc[c];
-        sts_f64(c_a + 8 * LD * (row_extra + e), sacc);
-      }
-    }
+    if (!RED) constraint_rows();
     phase_sync<PS>();
     const double clb_r = (DEBUG_OUT && lane < nC) ? lds_f64(clb_a + 8 * lane) : 0.0;
     const double cub_r = (DEBUG_OUT && lane < nC) ? lds_f64(cub_a + 8 * lane) : 0.0;
