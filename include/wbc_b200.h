@@ -230,6 +230,29 @@ int wbc_qp_solve(int64_t N, int32_t nv, int32_t m, int32_t nC, const double* A, 
 /* the fused tick */
 int wbc_step(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, int64_t N, void* stream);
 
+/* Host-side arrays of one tick for wbc_step_host: what a caller of the reference holds as NumPy arrays
+ * (runWBC's arguments and return values, Robot_Wrapper4.py:1330-1412).  Page-locked memory makes the copies
+ * asynchronous; pageable memory works but serialises them.  An input left NULL is not copied: it is resident in the
+ * device buffer of `io` already (e.g. the task memory and per-robot references, which the reference keeps as
+ * attributes of the controller object).  An output left NULL is not copied back. */
+typedef struct WbcHostIO {
+  const double* q;          /* [N, nq] */
+  const double* targets;    /* [N, 18] */
+  const double* mem_in;     /* [N, 72] or NULL */
+  const double* ref;        /* [N, 24] or NULL */
+  double* qdot;             /* [N, nv] */
+  int32_t* status;          /* [N] */
+  int32_t* iters;           /* [N] */
+} WbcHostIO;
+
+/* The open-loop tick with host buffers.  `io` names the device staging buffers (all of wbc_step's required members;
+ * q_next / mem_out / imu_quat / active_set must be NULL).  The batch is cut into `chunks` contiguous slices whose
+ * host->device copies, kernel and device->host copies overlap on three streams owned by the model (created on first
+ * use).  Asynchronous: `stream` is ordered before the first copy and after the last; synchronise it before reading
+ * the host outputs.  Not re-entrant per model handle. */
+int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const WbcHostIO* host, int64_t N,
+                  int32_t chunks, void* stream);
+
 /* Closed loop: K consecutive ticks (the tick loop of sim3.py:287-327 around runWBC, Robot_Wrapper4.py:1330-1412) for
  * N robots, one fused launch per tick, configuration and task memory advanced in place on the device.
  * io->q is read and overwritten (io->q_next must be NULL or equal to io->q), io->mem_in likewise (io->mem_out NULL or

@@ -32,7 +32,7 @@ JT_UNIVERSE, JT_FREEFLYER, JT_REVOLUTE, JT_PRISMATIC = 0, 1, 2, 3
 EXPORTS = [
     "wbc_abi_version", "wbc_last_error", "wbc_model_create", "wbc_model_destroy", "wbc_config_rows",
     "wbc_fk_jac", "wbc_joint_jacobians", "wbc_init_memory", "wbc_integrate", "wbc_assemble", "wbc_qp_solve", "wbc_step",
-    "wbc_rollout",
+    "wbc_rollout", "wbc_step_host",
     "wbc_step_launch_info", "wbc_measure_fp64_peak",
 ]
 
@@ -73,6 +73,11 @@ class WbcStepIO(C.Structure):
         ("qdot", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p), ("active_set", C.c_void_p),
         ("mem_out", C.c_void_p), ("q_next", C.c_void_p),
     ]
+
+
+class WbcHostIO(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("targets", C.c_void_p), ("mem_in", C.c_void_p), ("ref", C.c_void_p),
+                ("qdot", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p)]
 
 
 class WbcAssembleOut(C.Structure):
@@ -128,6 +133,7 @@ def load():
     lib.wbc_assemble.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), i64, C.POINTER(WbcAssembleOut), vp]
     lib.wbc_qp_solve.argtypes = [i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wbc_step.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), i64, vp]
+    lib.wbc_step_host.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), C.POINTER(WbcHostIO), i64, i32, vp]
     lib.wbc_rollout.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), vp, vp, i32, i64, vp]
     lib.wbc_step_launch_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.wbc_measure_fp64_peak.argtypes = [C.POINTER(f64), vp]

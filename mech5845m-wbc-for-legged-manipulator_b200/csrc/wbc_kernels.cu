@@ -22,11 +22,16 @@ static int fail(int code, const char* fmt, const char* detail = "") {
     if (e__ != cudaSuccess) return fail(WBC_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
   } while (0)
 
+#define WBC_PIPE_STREAMS 3
 struct WbcModel {
   DevModel host;
   DevModel* dev;
   int device;
   int sm_count;
+  // wbc_step_host: copy / compute pipeline (created on first use)
+  bool pipe_ready;
+  cudaStream_t pipe[WBC_PIPE_STREAMS];
+  cudaEvent_t pipe_start, pipe_done[WBC_PIPE_STREAMS];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -646,6 +651,7 @@ int wbc_model_create(const WbcTreeTable* table, WbcModel** out_model) {
   if (!table || !out_model) return fail(WBC_ERR_INVALID_ARG, "null argument%s");
   WbcModel* m = new (std::nothrow) WbcModel;
   if (!m) return fail(WBC_ERR_INVALID_ARG, "out of host memory%s");
+  m->pipe_ready = false;
   int rc = build_dev_model(table, &m->host);
   if (rc != WBC_OK) { delete m; return rc; }
   cudaError_t e = cudaGetDevice(&m->device);
@@ -662,6 +668,14 @@ int wbc_model_create(const WbcTreeTable* table, WbcModel** out_model) {
 
 void wbc_model_destroy(WbcModel* model) {
   if (!model) return;
+  if (model->pipe_ready) {
+    for (int s = 0; s < WBC_PIPE_STREAMS; ++s) {
+      cudaStreamSynchronize(model->pipe[s]);
+      cudaStreamDestroy(model->pipe[s]);
+      cudaEventDestroy(model->pipe_done[s]);
+    }
+    cudaEventDestroy(model->pipe_start);
+  }
   cudaFree(model->dev);
   delete model;
 }
@@ -755,6 +769,87 @@ int wbc_step(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, i
   if (N < 0 || !io->qdot || !io->status || !io->iters) return fail(WBC_ERR_INVALID_ARG, "qdot / status / iters are required%s");
   P.N = N;
   return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
+}
+
+// The fused tick for a caller that holds host arrays (the reference's calling convention: NumPy in, NumPy out,
+// Robot_Wrapper4.py:1330-1412).  The batch is cut into `chunks` slices; host -> device copies, the kernel and the
+// device -> host copies of consecutive slices overlap on three internal streams.  `stream` is ordered before the first
+// copy and after the last one.
+int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const WbcHostIO* host, int64_t N,
+                  int32_t chunks, void* stream) {
+  StepParams P;
+  int rc = check_cfg(model, cfg, io, &P);
+  if (rc != WBC_OK) return rc;
+  if (!host) return fail(WBC_ERR_INVALID_ARG, "null host io%s");
+  if (N < 0 || !io->qdot || !io->status || !io->iters) return fail(WBC_ERR_INVALID_ARG, "qdot / status / iters are required%s");
+  if (io->q_next || io->mem_out || io->imu_quat || io->active_set)
+    return fail(WBC_ERR_UNSUPPORTED, "wbc_step_host runs the open-loop tick (q_next / mem_out / imu_quat / active_set must be NULL)%s");
+  if (N == 0) return WBC_OK;
+  if (!model->pipe_ready) {
+    for (int s = 0; s < WBC_PIPE_STREAMS; ++s) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&model->pipe[s], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&model->pipe_done[s], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&model->pipe_start, cudaEventDisableTiming));
+    model->pipe_ready = true;
+  }
+  if (chunks < 1) chunks = 1;
+  if (chunks > N) chunks = (int32_t)N;
+  if (chunks > 64) chunks = 64;
+  // Slice boundaries: whole waves of the persistent kernel (one state per resident warp), so that no slice ends on a
+  // partly filled wave; the first and the last slice are a single wave -- they are the exposed parts of the pipeline
+  // (nothing overlaps the first copy in and the last copy out).
+  int64_t bnd[65];
+  {
+    int info[4] = {0, 0, 0, 0};
+    P.N = N;
+    rc = launch_step<false>(model, P, nullptr, info);
+    if (rc != WBC_OK) return rc;
+    const int64_t wave = (int64_t)info[0] * (info[1] / 32);
+    const int64_t W = (N + wave - 1) / wave;
+    if (chunks >= 3 && W >= chunks) {
+      bnd[0] = 0;
+      bnd[1] = wave;
+      for (int c = 2; c < chunks; ++c) bnd[c] = wave * (1 + (W - 2) * (c - 1) / (chunks - 2));
+      bnd[chunks] = N;
+    } else {
+      for (int c = 0; c <= chunks; ++c) bnd[c] = N * c / chunks;
+    }
+  }
+  const cudaStream_t user = (cudaStream_t)stream;
+  const int nq = model->host.nq, nv = model->host.nv;
+  CUDA_TRY(cudaEventRecord(model->pipe_start, user));
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t lo = bnd[c], hi = bnd[c + 1], n = hi - lo;
+    if (n <= 0) continue;
+    const cudaStream_t st = model->pipe[c % WBC_PIPE_STREAMS];
+    if (c < WBC_PIPE_STREAMS) CUDA_TRY(cudaStreamWaitEvent(st, model->pipe_start, 0));
+    struct { const double* h; const double* d; int stride; } in[4] = {
+        {host->q, io->q, nq}, {host->targets, io->targets, WBC_TARGETS_STRIDE},
+        {host->mem_in, io->mem_in, WBC_MEM_STRIDE}, {host->ref, io->ref, WBC_REF_STRIDE}};
+    for (int k = 0; k < 4; ++k)
+      if (in[k].h)                       // NULL: resident on the device already
+        CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(in[k].d) + lo * in[k].stride, in[k].h + lo * in[k].stride,
+                                 sizeof(double) * n * in[k].stride, cudaMemcpyHostToDevice, st));
+    P.io.q = io->q + lo * nq;
+    P.io.targets = io->targets + lo * WBC_TARGETS_STRIDE;
+    P.io.mem_in = io->mem_in + lo * WBC_MEM_STRIDE;
+    P.io.ref = io->ref + lo * WBC_REF_STRIDE;
+    P.io.qdot = io->qdot + lo * nv;
+    P.io.status = io->status + lo;
+    P.io.iters = io->iters + lo;
+    P.N = n;
+    rc = launch_step<false>(model, P, st, nullptr);
+    if (rc != WBC_OK) return rc;
+    if (host->qdot) CUDA_TRY(cudaMemcpyAsync(host->qdot + lo * nv, P.io.qdot, sizeof(double) * n * nv, cudaMemcpyDeviceToHost, st));
+    if (host->status) CUDA_TRY(cudaMemcpyAsync(host->status + lo, P.io.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (host->iters) CUDA_TRY(cudaMemcpyAsync(host->iters + lo, P.io.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < WBC_PIPE_STREAMS && s < chunks; ++s) {
+    CUDA_TRY(cudaEventRecord(model->pipe_done[s], model->pipe[s]));
+    CUDA_TRY(cudaStreamWaitEvent(user, model->pipe_done[s], 0));
+  }
+  return WBC_OK;
 }
 
 int wbc_rollout(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const double* targets_traj,

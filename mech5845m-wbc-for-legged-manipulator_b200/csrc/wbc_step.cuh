@@ -487,6 +487,12 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
   }
 }
 
+#ifndef WBC_SYNC_TOP
+#define WBC_SYNC_TOP 1         // phase barrier at the top of a tick (after the input prefetch has landed)
+#endif
+#ifndef WBC_SYNC_POSTQP
+#define WBC_SYNC_POSTQP 1      // phase barrier after the QP
+#endif
 #ifndef WBC_QP_MID_SYNC
 #define WBC_QP_MID_SYNC 0
 #endif
@@ -548,7 +554,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     const uint32_t q_a = in_a + 8 * WBC_IN_Q, tg_a = in_a + 8 * WBC_IN_TARGETS;
     const uint32_t mem_a = in_a + 8 * WBC_IN_MEM, ref_a = in_a + 8 * WBC_IN_REF;
     cp_async_wait_all();
-    phase_sync<PS>();
+    phase_sync<PS && (WBC_SYNC_TOP != 0)>();
 
     // ---------------------------------------------------------------- kinematics
     double Sc[6];                        // column `lane` of data.J (WORLD): [lin; ang]
@@ -969,7 +975,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
                                                                                     x, a, aj, bj);
     }
 
-    phase_sync<PS>();            // (measured: dropping this barrier costs 6 %)
+    phase_sync<PS && (WBC_SYNC_POSTQP != 0)>();
     if (valid && lane < NV) P.io.qdot[sidx * NV + lane] = x;
     if (valid && lane == 0) {
       P.io.status[sidx] = res.status;

@@ -630,55 +630,45 @@ class RobotModel:
 
         ``host_in``: dict of pinned float64 CPU tensors q [N, nq], targets [N, 18], mem [N, 72], ref [N, 24];
         ``host_out``: dict of pinned CPU tensors qdot [N, nv], status [N] (int32), iters [N] (int32).
-        The batch is cut into ``chunks`` contiguous slices that go host -> device, through the fused kernel and back
-        on three side streams, so the PCIe copies of one slice overlap the kernel of another; the current stream
-        waits for all of them.  Returns (h2d_bytes, d2h_bytes).
+        One C-ABI call (``wbc_step_host``): the batch is cut into ``chunks`` contiguous slices that go host -> device,
+        through the fused kernel and back on three streams owned by the model, so the PCIe copies of one slice overlap
+        the kernel of another; the current stream waits for all of them.  Returns (h2d_bytes, d2h_bytes).
 
         ``resident_state``: only the per-tick inputs (q, targets) travel; the task memory and the per-robot references
         stay where the reference keeps them -- in the controller object (``prev_EE_pos`` ... ``initial_trunk_pos``,
         Robot_Wrapper4.py:133-140, 363-383), i.e. on the device.
         """
         N = self.N
-        cfg = self._config()
-        cur = torch.cuda.current_stream(self.device)
-        if not hasattr(self, "_side_streams"):
-            self._side_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]
-        chunks = max(1, min(int(chunks), N))
-        bounds = [(N * c) // chunks for c in range(chunks + 1)]
-        dev_in = {"q": self.current_joint_config, "targets": self._targets, "mem": self._mem, "ref": self._ref}
         moved = ("q", "targets") if resident_state else ("q", "targets", "mem", "ref")
-        dev_out = {"qdot": self.qdot, "status": self.last_status, "iters": self.last_iters}
-        start = torch.cuda.Event()
-        start.record(cur)
-        done = []
+        for k in moved:
+            t = host_in[k]
+            if t.device.type != "cpu" or t.dtype != torch.float64 or not t.is_contiguous():
+                raise ValueError(f"host_in[{k!r}] must be a contiguous float64 CPU tensor")
+        for k, dt_ in (("qdot", torch.float64), ("status", torch.int32), ("iters", torch.int32)):
+            t = host_out[k]
+            if t.device.type != "cpu" or t.dtype != dt_ or not t.is_contiguous():
+                raise ValueError(f"host_out[{k!r}] must be a contiguous {dt_} CPU tensor")
+        io = cabi.WbcStepIO()
+        io.q = self.current_joint_config.data_ptr()
+        io.targets = self._targets.data_ptr()
+        io.mem_in = self._mem.data_ptr()
+        io.ref = self._ref.data_ptr()
+        io.dt = float(self.dt)
+        io.qdot = self.qdot.data_ptr()
+        io.status = self.last_status.data_ptr()
+        io.iters = self.last_iters.data_ptr()
+        host = cabi.WbcHostIO()
+        host.q = host_in["q"].data_ptr()
+        host.targets = host_in["targets"].data_ptr()
+        if not resident_state:
+            host.mem_in = host_in["mem"].data_ptr()
+            host.ref = host_in["ref"].data_ptr()
+        host.qdot = host_out["qdot"].data_ptr()
+        host.status = host_out["status"].data_ptr()
+        host.iters = host_out["iters"].data_ptr()
         with torch.cuda.device(self.device):
-            for c in range(chunks):
-                lo, hi = bounds[c], bounds[c + 1]
-                if hi == lo:
-                    continue
-                st = self._side_streams[c % len(self._side_streams)]
-                st.wait_event(start)
-                with torch.cuda.stream(st):
-                    for k in moved:
-                        dev_in[k][lo:hi].copy_(host_in[k][lo:hi], non_blocking=True)
-                    io = cabi.WbcStepIO()
-                    io.q = dev_in["q"][lo:hi].data_ptr()
-                    io.targets = dev_in["targets"][lo:hi].data_ptr()
-                    io.mem_in = dev_in["mem"][lo:hi].data_ptr()
-                    io.ref = dev_in["ref"][lo:hi].data_ptr()
-                    io.dt = float(self.dt)
-                    io.qdot = dev_out["qdot"][lo:hi].data_ptr()
-                    io.status = dev_out["status"][lo:hi].data_ptr()
-                    io.iters = dev_out["iters"][lo:hi].data_ptr()
-                    cabi.check(self._lib.wbc_step(self._model, C.byref(cfg), C.byref(io), hi - lo,
-                                                  C.c_void_p(st.cuda_stream)))
-                    for k in dev_out:
-                        host_out[k][lo:hi].copy_(dev_out[k][lo:hi], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    done.append(ev)
-        for ev in done:
-            cur.wait_event(ev)
+            cabi.check(self._lib.wbc_step_host(self._model, C.byref(self._config()), C.byref(io), C.byref(host), N,
+                                               int(chunks), _stream_ptr()))
         h2d = sum(host_in[k].numel() * 8 for k in moved)
         d2h = host_out["qdot"].numel() * 8 + host_out["status"].numel() * 4 + host_out["iters"].numel() * 4
         return h2d, d2h

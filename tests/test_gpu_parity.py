@@ -376,6 +376,35 @@ def test_com_rows_match_oracle():
     assert np.abs(x[ok] - cref["qdot"][ok]).max() < QP_TOL
 
 
+@pytest.mark.parametrize("resident", [True, False])
+def test_step_host_matches_device_step(resident):
+    """wbc_step_host (host buffers in, host buffers out, sliced copy / compute pipeline inside the C ABI) returns exactly
+    what the device-resident tick returns, for a batch that does not divide into the slices and for more slices than
+    three streams."""
+    name, N = "a1_wx200", 4099
+    robot = _robot(name, N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260011, 5e-3)
+    mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=False).clone()
+    st, it = robot.last_status.clone(), robot.last_iters.clone()
+    host_in = {"q": robot.current_joint_config.cpu().pin_memory(), "targets": targets.cpu().pin_memory(),
+               "mem": mem0.cpu().pin_memory(), "ref": ref0.cpu().pin_memory()}
+    host_out = {"qdot": torch.full((N, robot.n_velocity_dimensions), float("nan"), dtype=torch.float64).pin_memory(),
+                "status": torch.full((N,), -1, dtype=torch.int32).pin_memory(),
+                "iters": torch.full((N,), -1, dtype=torch.int32).pin_memory()}
+    if not resident:                     # everything travels: scramble the device copies first
+        robot.current_joint_config.zero_(); robot._targets.zero_(); robot._mem.zero_(); robot._ref.zero_()
+    else:                                # task memory / references resident; q and targets travel
+        robot.current_joint_config.zero_(); robot._targets.zero_()
+    for chunks in (1, 7):
+        host_out["qdot"].fill_(float("nan"))
+        h2d, d2h = robot.step_host(host_in, host_out, chunks=chunks, resident_state=resident)
+        torch.cuda.synchronize()
+        assert torch.equal(host_out["qdot"], x.cpu())
+        assert torch.equal(host_out["status"], st.cpu()) and torch.equal(host_out["iters"], it.cpu())
+        assert h2d == N * 8 * ((27 + 18) if resident else (27 + 18 + 72 + 24)) and d2h == N * (26 * 8 + 8)
+
+
 def test_ragged_and_empty_batches():
     """Batch-size invariance: a state's answer does not depend on how many other states ride in the launch
     (1, 13, one more than a full wave of 148 x 12 warps), and an empty batch is a no-op."""
