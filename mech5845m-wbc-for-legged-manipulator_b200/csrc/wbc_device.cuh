@@ -261,8 +261,10 @@ __device__ __forceinline__ void scipy_quat_from_matrix(const double* Rin, double
   } else {
     q[0] = R[7] - R[5]; q[1] = R[2] - R[6]; q[2] = R[3] - R[1]; q[3] = 1 + tr;
   }
-  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+  // (SciPy divides by the norm; multiplying by rsqrt(|q|^2) differs by <= 2 ulp and saves a square root and four
+  //  divisions, ~130 instructions of every tick)
+  const double rn = rsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= rn; q[1] *= rn; q[2] *= rn; q[3] *= rn;
 }
 
 __device__ __forceinline__ void quat_compose(const double* p, const double* q, double* o) {  // o = p * q

@@ -559,8 +559,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
           if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
         }
         if (bidx == 0x7fffffff) best = 0.0;
+        if (!__any_sync(WBC_FULL_MASK, best < -WBC_QP_FEAS_TOL)) break;   // primal feasible: optimal (the usual exit)
         warp_argmin(best, bidx);
-        if (!(best < -WBC_QP_FEAS_TOL)) break;                     // primal feasible: optimal
         ip = bidx;
         const int src = (ip < n) ? ip : ip - n;
         side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);
@@ -649,8 +649,10 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
       // dual step length over active inequalities
       double t1 = INFINITY;
       int l = 0x7fffffff;
-      if (lane >= p_eq && lane < iq && rr > 0.0) { t1 = u / rr; l = lane; }
-      warp_argmin(t1, l);
+      if (iq > p_eq) {                                               // (no active inequality: nothing can block the step)
+        if (lane >= p_eq && lane < iq && rr > 0.0) { t1 = u / rr; l = lane; }
+        warp_argmin(t1, l);
+      }
       const double t = fmin(t1, t2);
       if (!(t < INFINITY)) { res.status |= WBC_QP_INFEASIBLE; break; }
       if (lane >= p_eq && lane < iq) u -= t * rr;
