@@ -313,8 +313,11 @@ __device__ __forceinline__ void scipy_matrix_from_quat(const double* q, double* 
 }
 
 __device__ __forceinline__ double wrap_pi(double a) {  // (a + pi) % (2 pi) - pi, floor-mod
+  // |a| <= 2 pi for every caller (sums / differences of atan2 results), so one fold replaces fmod; r - 2 pi is exact
+  // (Sterbenz), i.e. the result is bit-identical to the fmod form
   const double pi = 3.141592653589793, two_pi = 6.283185307179586;
-  double r = fmod(a + pi, two_pi);
+  double r = a + pi;
+  if (r >= two_pi) r -= two_pi;
   if (r < 0) r += two_pi;
   return r - pi;
 }
@@ -346,7 +349,8 @@ __device__ __forceinline__ void warp_scipy_euler_xyz_from_quat(const double* q, 
   const double pi = 3.141592653589793;
   const double a = q[3] - q[1], b = q[0] + q[2], c = q[1] + q[3], d = q[2] - q[0];
   const int r = lane % 3;
-  const double h = hypot((lane & 1) ? a : c, (lane & 1) ? b : d);   // lane 0: hypot(c, d), lane 1: hypot(a, b)
+  const double hx = (lane & 1) ? a : c, hy = (lane & 1) ? b : d;    // lane 0: hypot(c, d), lane 1: hypot(a, b)
+  const double h = sqrt(fma(hx, hx, hy * hy));                      // (|q| = 1: no overflow to guard against; <= 1 ulp from hypot)
   const double hcd = __shfl_sync(WBC_FULL_MASK, h, 0), hab = __shfl_sync(WBC_FULL_MASK, h, 1);
   const double ty = (r == 0) ? b : ((r == 1) ? d : hcd);
   const double tx = (r == 0) ? a : ((r == 1) ? c : hab);

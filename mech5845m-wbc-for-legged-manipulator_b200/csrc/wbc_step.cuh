@@ -303,15 +303,16 @@ __device__ __forceinline__ void damper_bounds_a(uint32_t M_a, const WbcConfig& c
   const double vel = (k < 7) ? 5.0 : lds_f64(M_a + WBC_MOFF(velocity) + 8 * k);   // vel_lim[i] = 5 for i < 7 (:593)
   const double c = lds_f64(q_a + 8 * ((cfg.compat_flags & WBC_COMPAT_DAMPER_OFF_BY_ONE) ? k : qidx));   // quirk D.2
   const double coef = cfg.damper_coef, qi = cfg.damper_qi, qsv = cfg.damper_qs;
+  const double inv_zone = 1.0 / (qi - qsv);      // uniform over the launch (hoisted); x * (1 / d) is within 1 ulp of x / d
   if (c <= lo + qi) {
-    lbv = -coef * (c - lo - qsv) / (qi - qsv);
+    lbv = (-coef * (c - lo - qsv)) * inv_zone;
     if (lbv > vel) lbv = vel;
     if (lbv < -vel) lbv = -vel;
   } else {
     lbv = -vel;
   }
   if (c >= up - qi) {
-    ubv = coef * (up - c - qsv) / (qi - qsv);
+    ubv = (coef * (up - c - qsv)) * inv_zone;
     if (ubv < -vel) ubv = -vel;
     if (ubv > vel) ubv = vel;
   } else {
