@@ -498,7 +498,9 @@ def run_ours(args):
                          "peak_source": "measured in this run: DFMA-saturating microkernel (wbc_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_state": {"fk_jac_targets": f_fkj, "AtA_sym_dense": f_asm, "qp": f_qp, "total": f_step},
-                         "note": "algorithmic flops per SURVEY 8d (dense symmetric A^T A); the kernel skips structural zeros"},
+                         "note": "algorithmic flops per SURVEY 8d (dense symmetric A^T A, Cholesky of the full H, k-bar working-set "
+                                 "changes on the full factor); the kernel does fewer: it skips the structural zeros of A and "
+                                 "eliminates the twelve foot equality rows up front (11 x 11 reduced Hessian, DESIGN 4.2)"},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_state * n_local / kern_s / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": bytes_state * n_local / kern_s / 1e9 / hbm_peak,
                              "bytes_per_state": bytes_state,

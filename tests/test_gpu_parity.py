@@ -333,6 +333,31 @@ def test_reduced_front_against_c_oracle_and_general_front(name, kind, monkeypatc
     assert same_path.mean() > 0.995 and same_set.mean() > 0.995, (same_path.mean(), same_set.mean())
 
 
+def test_reduced_front_falls_back_on_singular_legs(monkeypatch):
+    """States whose leg Jacobian is (nearly) singular -- a straight knee, calf angle 0 -- fail the conditioning check of
+    the reduced front and take the general front inside the same launch; every state, singular or not, must agree with
+    the launch that has the reduced front switched off."""
+    N = 1024
+    name = "a1_wx200"
+    robot = _robot(name, N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260013, 5e-3)
+    qd = robot.current_joint_config.clone()
+    calf = [robot.robot_model.idx_q[robot.robot_model.getJointId(n)] for n in ("FL_calf_joint", "RR_calf_joint")]
+    qd[::7, calf[0]] = 0.0                         # every 7th state: FL knee straight
+    qd[3::11, calf[1]] = 1e-7                      # some: RR knee within 1e-7 rad of straight
+    robot.current_joint_config.copy_(qd)            # (task memory / references stay those of the sampled states)
+    ee, tr = targets[:, :15].reshape(N, 5, 3), targets[:, 15:18]
+    x_red = robot.step(ee, tr, advance=False).clone()
+    st_red, it_red, act_red = robot.last_status.clone(), robot.last_iters.clone(), robot.last_active_set.clone()
+    monkeypatch.setenv("WBC_B200_NO_REDUCED", "1")
+    x_gen = robot.step(ee, tr, advance=False).clone()
+    assert torch.equal(st_red, robot.last_status)
+    ok = robot.last_status == 0                    # (a straight knee makes the foot rows dependent: the general front
+    assert ok.double().mean() > 0.8                #  may flag such states; both launches must flag the same ones)
+    assert (x_red[ok] - x_gen[ok]).abs().max() < 1e-7
+    assert torch.equal(it_red[ok], robot.last_iters[ok]) and torch.equal(act_red[ok], robot.last_active_set[ok])
+
+
 def test_bootstrap_matches_oracle():
     """f4: the constructor bootstrap (setInitialState, Robot_Wrapper4.py:196-351) batched -- 60 of its 2000 ticks
     (linear EE trajectories, bounds-only QP, plain integrate) and the final re-basing, against the oracle."""
