@@ -355,14 +355,15 @@ def run_ours(args):
                 "iters": torch.empty(n_local, dtype=torch.int32, **pin)}
     e2e_steps = max(3, min(args.steps, 10))
 
+    E2E_CHUNKS = int(os.environ.get("WBC_E2E_CHUNKS", "8"))     # slices of the copy / compute pipeline (wbc_step_host)
     def e2e_leg(resident_state):
         for _ in range(3):
-            h2d_, d2h_ = robot.step_host(host_in, host_out, resident_state=resident_state)
+            h2d_, d2h_ = robot.step_host(host_in, host_out, chunks=E2E_CHUNKS, resident_state=resident_state)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(e2e_steps):
-            robot.step_host(host_in, host_out, resident_state=resident_state)
+            robot.step_host(host_in, host_out, chunks=E2E_CHUNKS, resident_state=resident_state)
         e1.record()
         barrier()
         t_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
