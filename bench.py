@@ -293,7 +293,9 @@ def run_ours(args):
     mem0 = robot._mem.clone()
 
     def one_step():
-        robot.step(ee_t, tr_t, advance=False)
+        # q, targets, task memory, references in; qdot, status, iters out: the 1344 B/state of SURVEY 8d (the active-set
+        # masks, an extension the reference does not return, are left to the verification pass below)
+        robot.step(ee_t, tr_t, advance=False, report_active_set=False)
 
     def barrier():
         if world > 1:

@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
     QpRegShared S;
     S.R = smem_addr(Hs); S.col = smem_addr(col); S.vd = smem_addr(vd); S.C = smem_addr(Cs);
     S.clb = smem_addr(bnd); S.cub = S.clb + 8 * 32; S.dd = S.clb + 8 * 64;
+    S.red_rows = S.feet_mask = S.red_blk = S.b = 0; S.skip_act = P.active_set == nullptr;
     double x;
     const QpResult res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, P.max_iter, x);
     if (lane < n) P.x[s * n + lane] = x;

@@ -50,6 +50,7 @@ struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byt
   uint32_t red_rows, feet_mask;
   uint32_t red_blk;  // 2 bits per foot task t: j of its limb columns [6 + 3 j, 9 + 3 j)
   uint32_t b;        // [36] targets of the Cartesian task rows
+  uint32_t skip_act; // non-zero: the caller does not want the active-set bit masks (QpResult::act_box / act_rows stay 0)
 };
 
 // 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free
@@ -782,7 +783,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
   else ineq_loop(QpIntC<0>{});
 
   x_out = (fixed || sfix) ? lds_f64(lo_a + 8 * lane) : x;
-  pack_active_sets(lane, NQ + NF, nC, bstat, cstat, res);
+  res.act_box = res.act_rows = 0ull;
+  if (!S.skip_act) pack_active_sets(lane, NQ + NF, nC, bstat, cstat, res);   // (~130 instructions: only on request)
   return res;
 }
 

@@ -971,7 +971,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
       S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
       S.red_rows = P.red_rows; S.feet_mask = P.red_feet_mask; S.red_blk = P.red_blk;
-      S.b = bs_a;
+      S.b = bs_a; S.skip_act = P.io.active_set == nullptr;
       res = warp_qp_solve_reg_impl<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF, RED>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter,
                                                                                     x, a, aj, bj);
     }

@@ -604,19 +604,21 @@ class RobotModel:
 
     # ---------------------------------------------------------------------------------- the fused tick :1330-1412
     def step(self, target_cartesian_pos_EE, target_cartesian_pos_trunk, imu_quat=None, advance=True,
-             plain_integrate=False, constraint_mask=None):
+             plain_integrate=False, constraint_mask=None, report_active_set=True):
         """One fused launch: FK + Jacobians + task stack + bounds + constraints + QP (+ integrate / base estimate).
 
         Returns qdot [N, nv]; ``last_status`` / ``last_iters`` / ``last_active_set`` hold the per-state QP report.
         With ``advance`` the task memory and ``current_joint_config`` move on in place, as runWBC does.
+        ``report_active_set=False``: only what the reference's ``solveQP`` returns (the primal solution) plus status and
+        iteration count; the active-set bit masks (an extension, 16 B per state) are not packed and not written.
         """
         T = self._pack_targets(target_cartesian_pos_EE, target_cartesian_pos_trunk)
         cfg = self._config(constraint_mask=constraint_mask)
         imu = self._as_batch(imu_quat, 4) if imu_quat is not None else None
         q_next = torch.empty_like(self.current_joint_config) if advance else None
         io = self._io(targets=T, qdot=self.qdot, status=self.last_status, iters=self.last_iters,
-                      active_set=self.last_active_set, mem_out=self._mem if advance else None, q_next=q_next,
-                      imu_quat=imu)
+                      active_set=self.last_active_set if report_active_set else None,
+                      mem_out=self._mem if advance else None, q_next=q_next, imu_quat=imu)
         io.flags = cabi.STEP_FLAG_PLAIN_INTEGRATE if plain_integrate else 0
         with torch.cuda.device(self.device):
             cabi.check(self._lib.wbc_step(self._model, C.byref(cfg), C.byref(io), self.N, _stream_ptr()))
