@@ -357,7 +357,7 @@ def run_ours(args):
                 "iters": torch.empty(n_local, dtype=torch.int32, **pin)}
     e2e_steps = max(3, min(args.steps, 10))
 
-    E2E_CHUNKS = int(os.environ.get("WBC_E2E_CHUNKS", "8"))     # slices of the copy / compute pipeline (wbc_step_host)
+    E2E_CHUNKS = int(os.environ.get("WBC_E2E_CHUNKS", "0"))     # 0: zero-copy from / to pinned host memory; n >= 1: n staged slices
     def e2e_leg(resident_state):
         for _ in range(3):
             h2d_, d2h_ = robot.step_host(host_in, host_out, chunks=E2E_CHUNKS, resident_state=resident_state)
@@ -484,14 +484,16 @@ def run_ours(args):
             "ns_per_state": 1e6 * total_ms_max / args.steps / n_global * world,
             "p50_single_state_step_us": lat_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "RobotModel.step_host(resident_state=True) -> wbc_step (C ABI): q and targets from "
+                    "steps": e2e_steps, "api": "RobotModel.step_host(resident_state=True) -> wbc_step_host (C ABI): q and targets from "
                                                   "pinned host buffers every step, qdot / status / iters back to the host; task memory "
                                                   "and per-robot references stay in the controller object (device), as the reference "
-                                                  "keeps them as attributes; 8 slices pipelined over 3 streams",
-                    "gpu_launches_per_step": 8,
+                                                  "keeps them as attributes; " + ("zero-copy: the kernel reads / writes the pinned host "
+                                                  "buffers over PCIe itself, one launch" if E2E_CHUNKS <= 0 else
+                                                  f"{E2E_CHUNKS} staged slices pipelined over 3 streams"),
+                    "gpu_launches_per_step": 1 if E2E_CHUNKS <= 0 else E2E_CHUNKS,
                     "all_inputs_from_host": {"value": e2e_all_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all,
                                              "d2h_bytes_per_step": d2h_all,
-                                             "note": "q, targets, task memory and references all copied every step (PCIe-bound)"}},
+                                             "note": "q, targets, task memory and references all cross PCIe every step (PCIe-bound)"}},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp64_fma", "achieved": ach_tflops, "peak": peak.value / 1e12, "unit": "TFLOP/s",

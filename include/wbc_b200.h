@@ -245,11 +245,15 @@ typedef struct WbcHostIO {
   int32_t* iters;           /* [N] */
 } WbcHostIO;
 
-/* The open-loop tick with host buffers.  `io` names the device staging buffers (all of wbc_step's required members;
- * q_next / mem_out / imu_quat / active_set must be NULL).  The batch is cut into `chunks` contiguous slices whose
- * host->device copies, kernel and device->host copies overlap on three streams owned by the model (created on first
- * use).  Asynchronous: `stream` is ordered before the first copy and after the last; synchronise it before reading
- * the host outputs.  Not re-entrant per model handle. */
+/* The open-loop tick with host buffers.  `io` names the device buffers (all of wbc_step's required members;
+ * q_next / mem_out / imu_quat / active_set must be NULL); those of the travelling members are staging space whose
+ * contents are unspecified afterwards.
+ *   chunks <= 0  automatic: if every host array is page-locked the kernel reads the inputs from and writes the outputs
+ *                to host memory directly (zero-copy, one launch on `stream`); otherwise as chunks = 8;
+ *   chunks >= 1  staged: the batch is cut into `chunks` wave-aligned slices whose host->device copies, kernel and
+ *                device->host copies overlap on three streams owned by the model (created on first use).
+ * Asynchronous: `stream` is ordered before the first access and after the last; synchronise it before reading the host
+ * outputs.  Not re-entrant per model handle. */
 int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const WbcHostIO* host, int64_t N,
                   int32_t chunks, void* stream);
 

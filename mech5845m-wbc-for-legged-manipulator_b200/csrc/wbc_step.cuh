@@ -77,6 +77,7 @@ struct StepParams {
   // owning limb columns [6 + 3 j, 9 + 3 j) (one byte per j), bit mask of the foot rows; set_reduced()
   int red_ok;
   unsigned red_rows, red_feet_mask, red_blk;
+  int grid_cap;                                   // > 0: at most this many CTAs (wbc_step_host runs two slices side by side)
 };
 
 // Row layout of C implied by the constraint mask (findConstraints order, Robot_Wrapper4.py:764-836): computed once on

@@ -627,14 +627,16 @@ class RobotModel:
             self.current_joint_config = q_next
         return self.qdot
 
-    def step_host(self, host_in, host_out, chunks=8, resident_state=False):
+    def step_host(self, host_in, host_out, chunks=0, resident_state=False):
         """The fused tick with HOST buffers (what a caller holding NumPy arrays pays end to end).
 
         ``host_in``: dict of pinned float64 CPU tensors q [N, nq], targets [N, 18], mem [N, 72], ref [N, 24];
         ``host_out``: dict of pinned CPU tensors qdot [N, nv], status [N] (int32), iters [N] (int32).
-        One C-ABI call (``wbc_step_host``): the batch is cut into ``chunks`` contiguous slices that go host -> device,
-        through the fused kernel and back on three streams owned by the model, so the PCIe copies of one slice overlap
-        the kernel of another; the current stream waits for all of them.  Returns (h2d_bytes, d2h_bytes).
+        One C-ABI call (``wbc_step_host``).  ``chunks=0`` (default): with page-locked tensors the kernel reads the
+        inputs from and writes the outputs to host memory directly (zero-copy, one launch); with pageable tensors, or
+        ``chunks >= 1``, the batch is cut into contiguous slices that go host -> device, through the fused kernel and
+        back on three streams owned by the model, so the PCIe copies of one slice overlap the kernel of another; the
+        current stream waits for all of them.  Returns (h2d_bytes, d2h_bytes): the bytes that cross PCIe either way.
 
         ``resident_state``: only the per-tick inputs (q, targets) travel; the task memory and the per-robot references
         stay where the reference keeps them -- in the controller object (``prev_EE_pos`` ... ``initial_trunk_pos``,

@@ -421,7 +421,7 @@ def test_step_host_matches_device_step(resident):
         robot.current_joint_config.zero_(); robot._targets.zero_(); robot._mem.zero_(); robot._ref.zero_()
     else:                                # task memory / references resident; q and targets travel
         robot.current_joint_config.zero_(); robot._targets.zero_()
-    for chunks in (1, 7):
+    for chunks in (0, 1, 7):              # zero-copy, one staged slice, more slices than streams
         host_out["qdot"].fill_(float("nan"))
         h2d, d2h = robot.step_host(host_in, host_out, chunks=chunks, resident_state=resident)
         torch.cuda.synchronize()
