@@ -579,8 +579,9 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       if (on) {
         double Jc[6], fp[3];
         lds_vec3(omf_a + 8 * (WBC_T_STRIDE * t + 9), fp);
-        frame_jac_lwa(Sc, (supp[t] >> lane) & 1u, fp, t == 5, Jc);
-        const double w = cfg.cart_task_weight[t];
+        // (outside the frame's support the column is zero: folded into the scalar weight, one select instead of six)
+        frame_jac_lwa(Sc, true, fp, t == 5, Jc);
+        const double w = ((supp[t] >> lane) & 1u) ? cfg.cart_task_weight[t] : 0.0;
         if (w_ident) {
 #pragma unroll
           for (int r = 0; r < 6; ++r) a[6 * t + r] = Jc[r] * w;
