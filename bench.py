@@ -180,6 +180,8 @@ def time_cpu_port(name, arrays, dt, cores, min_seconds):
     q, targets, mem, ref = arrays
     chunks = [c for c in np.array_split(np.arange(q.shape[0]), cores) if len(c)]
     jobs = [(name, q[c], targets[c], mem[c], ref[c], dt, min_seconds) for c in chunks]
+    from oracle import c_port
+    c_port.build()                                       # once, here: not by every worker at the same time
     t0 = time.perf_counter()
     res = _pool_map(_c_worker, jobs)
     wall = time.perf_counter() - t0

@@ -25,11 +25,15 @@ def build(force=False):
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
         return LIB
     os.makedirs(BUILD_DIR, exist_ok=True)
+    # compile to a private name and rename: several processes (the bench's CPU-baseline workers, pytest-xdist) may find
+    # the library stale at the same time, and a reader must never see a half-written file
+    tmp = f"{LIB}.{os.getpid()}.tmp"
     cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "include"), SRC,
-           "-o", LIB, "-lm"]
+           "-o", tmp, "-lm"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("gcc failed:\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, LIB)
     return LIB
 
 
