@@ -53,6 +53,9 @@ struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byt
   uint32_t skip_act; // non-zero: the caller does not want the active-set bit masks (QpResult::act_box / act_rows stay 0)
 };
 
+#ifndef WBC_NEWTON_POLISH
+#define WBC_NEWTON_POLISH 1    // second (polishing) Newton step of fast_rsqrt / fast_rcp
+#endif
 // 1/sqrt(x) and 1/x for normal positive / non-zero finite x: hardware seed + Newton steps, branch-free
 // (the library rsqrt()/division carry a slow path for denormals that costs convergence barriers and
 // ~30 dependent instructions in the middle of every iteration).  Relative error <= ~2 ulp.
@@ -61,8 +64,10 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x * y, y, 1.0);                      // 1 - x y^2
   y = fma(y * fma(e, 0.375, 0.5), e, y);               // y (1 + e/2 + 3 e^2/8)
+#if WBC_NEWTON_POLISH
   e = fma(-x * y, y, 1.0);
   y = fma(y * 0.5, e, y);
+#endif
   return y;
 }
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -70,8 +75,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
   y = fma(y, fma(e, e, e), y);                         // y (1 + e + e^2)
+#if WBC_NEWTON_POLISH
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
+#endif
   return y;
 }
 
@@ -544,25 +551,26 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
     if (!have) {
       // ------------------------------------------------------------ pick the entering constraint
       {
-        double best = 0.0;
-        int bidx = 0x7fffffff;
+        // most violated side over the boxes (index lane) and the rows (index n + lane), ties to the lowest index:
+        // a min-reduction of the value, then two votes (every box index is below every row index)
+        double vb = INFINITY, vc = INFINITY;
         int myside_b = -1, myside_c = -1;
         if (act && bstat == 0) {
           const double slo = x - lds_f64(lo_a + 8 * lane), sup = lds_f64(up_a + 8 * lane) - x;
-          best = fmin(slo, sup);
-          bidx = lane;
+          vb = fmin(slo, sup);
           myside_b = (slo <= sup) ? -1 : +1;
         }
         if (lane < nC && cstat == 0) {
           const double slo = ax - lds_f64(S.clb + 8 * lane), sup = lds_f64(S.cub + 8 * lane) - ax;
-          const double v = fmin(slo, sup);
+          vc = fmin(slo, sup);
           myside_c = (slo <= sup) ? -1 : +1;
-          if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
         }
-        if (bidx == 0x7fffffff) best = 0.0;
+        double best = fmin(vb, vc);
         if (!__any_sync(WBC_FULL_MASK, best < -WBC_QP_FEAS_TOL)) break;   // primal feasible: optimal (the usual exit)
-        warp_argmin(best, bidx);
-        ip = bidx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(WBC_FULL_MASK, best, o));
+        const unsigned wb = __ballot_sync(WBC_FULL_MASK, vb == best), wc = __ballot_sync(WBC_FULL_MASK, vc == best);
+        ip = wb ? __ffs(wb) - 1 : n + __ffs(wc) - 1;
         const int src = (ip < n) ? ip : ip - n;
         side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);
       }
@@ -651,8 +659,13 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
       double t1 = INFINITY;
       int l = 0x7fffffff;
       if (iq > p_eq) {                                               // (no active inequality: nothing can block the step)
-        if (lane >= p_eq && lane < iq && rr > 0.0) { t1 = u / rr; l = lane; }
-        warp_argmin(t1, l);
+        const bool blk = lane >= p_eq && lane < iq && rr > 0.0;
+        double mine = blk ? u / rr : INFINITY;
+        t1 = mine;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t1 = fmin(t1, __shfl_xor_sync(WBC_FULL_MASK, t1, o));
+        const unsigned wl = __ballot_sync(WBC_FULL_MASK, blk && mine == t1);        // ties to the earliest position
+        l = wl ? __ffs(wl) - 1 : 0x7fffffff;
       }
       const double t = fmin(t1, t2);
       if (!(t < INFINITY)) { res.status |= WBC_QP_INFEASIBLE; break; }

@@ -492,6 +492,12 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 #ifndef WBC_SYNC_TOP
 #define WBC_SYNC_TOP 1         // phase barrier at the top of a tick (after the input prefetch has landed)
 #endif
+#ifndef WBC_SYNC_KIN
+#define WBC_SYNC_KIN 1         // phase barrier after the kinematics
+#endif
+#ifndef WBC_SYNC_PREQP
+#define WBC_SYNC_PREQP 1       // phase barrier before the QP
+#endif
 #ifndef WBC_SYNC_POSTQP
 #define WBC_SYNC_POSTQP 1      // phase barrier after the QP
 #endif
@@ -562,7 +568,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     double Sc[6];                        // column `lane` of data.J (WORLD): [lin; ang]
     double com_w[3], Jcom[2];
     warp_kin_a<NV>(M_a, q_a, omi_a, omf_a, lane, (cfg.constraint_mask & WBC_CON_COM) != 0, Sc, com_w, Jcom);
-    phase_sync<PS>();
+    phase_sync<PS && (WBC_SYNC_KIN != 0)>();
 
     // ---------------------------------------------------------------- task rows for my column (registers)
     // EE tasks: A = W (J_LWA w) (:476-482); trunk task: A = (W J_WORLD) w (:488-490)
@@ -932,7 +938,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     }
 
     if (!RED) constraint_rows();
-    phase_sync<PS>();
+    phase_sync<PS && (WBC_SYNC_PREQP != 0)>();
     const double clb_r = (DEBUG_OUT && lane < nC) ? lds_f64(clb_a + 8 * lane) : 0.0;
     const double cub_r = (DEBUG_OUT && lane < nC) ? lds_f64(cub_a + 8 * lane) : 0.0;
 
