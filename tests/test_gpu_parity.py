@@ -43,7 +43,7 @@ def _load(robot, N, seed, sigma):
     return q, targets
 
 
-@pytest.mark.parametrize("name", ["a1_wx200", "a1_px100_pin_ver"])
+@pytest.mark.parametrize("name", ["a1_wx200", "a1_px100_pin_ver", "laikago_vx300"])
 def test_fk_and_frame_jacobians_match_oracle(name):
     import wbc_b200
     from wbc_b200 import synthetic
@@ -104,6 +104,8 @@ def test_golden_jacobians_neutral_wx200():
     ("a1_px100_pin_ver", P2_TASKS, P2_CONS, "HYBRID", 5e-4),  # what sim3.py:145 actually runs (f2): FD manipulability gradient
     ("a1_wx200", P1_TASKS, P2_CONS, "HYBRID", 5e-4),
     ("a1_wx200", P2_TASKS, P2_CONS, "MANI", 5e-4),
+    ("laikago_vx300", P1_TASKS, P2_CONS, True, 5e-4),         # third robot of sim3.py:13 (joint rpy != 0, no `gripper` joint:
+                                                               #  the reference's look-up returns njoints, nothing gets locked)
 ])
 def test_assembly_and_qp_match_oracle(name, tasks, cons, joint, sigma):
     N = 96 if joint in (True, "PREV") else (32 if joint == "HYBRID" else 12)    # the FD modes cost 12 / 52 oracle FK passes per state

@@ -110,7 +110,7 @@ def test_standing_configs_and_mocap_rows_are_inside_limits():
 
 
 # ------------------------------------------------------------------------------------------------ kinematics invariants
-@pytest.mark.parametrize("name", ROBOTS)
+@pytest.mark.parametrize("name", ROBOTS + ["laikago_vx300"])      # (laikago: joint placements with rpy != 0)
 def test_frame_jacobians_equal_finite_differences_of_fk(name):
     """LOCAL_WORLD_ALIGNED frame Jacobian == d/de FK(integrate(q, e_k eps)) (Pinocchio semantics)."""
     model = H.oracle_model(name)

@@ -4,7 +4,7 @@
 Run in the build container:   python tools/make_fixtures.py [--reference /root/reference]
 
 Writes
-  <package>/data/a1_wx200.json, a1_px100_pin_ver.json   tree tables extracted by the PRODUCT's URDF walker
+  <package>/data/a1_wx200.json, a1_px100_pin_ver.json, laikago_vx300.json   tree tables extracted by the PRODUCT's URDF walker
                                                         (tree_table.TreeTable.from_urdf)
   tests/golden/jacobians_neutral_wx200.json             the reference's recorded Pinocchio output
                                                         tests_NOT_FOR_USE/Jacobians.py:1-24 (+ CoM block :27-42)
@@ -50,7 +50,7 @@ def main():
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
 
-    for name in ("a1_wx200", "a1_px100_pin_ver"):
+    for name in ("a1_wx200", "a1_px100_pin_ver", "laikago_vx300"):
         t = tt.TreeTable.from_urdf(os.path.join(ref, "Robot_Descriptions", "urdf", name + ".urdf"))
         t.save(os.path.join(PKG, "data", name + ".json"))
         print(name, "nq", t.nq, "nv", t.nv, "njoints", t.njoints, "nframes", t.nframes)
