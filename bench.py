@@ -234,7 +234,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, per_gpu_states=done // max(args.steps, 1)),
+        "config": workload_config(args, per_gpu_states=args.states),     # the same config as our arm; the bounded sample is in cpu_baseline.sample
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{done} ticks over {args.steps} steps (512 distinct states looped ~1 s per core per step): "
                                    f"oracle/wbc_oracle.c (plain-C restatement of Robot_Wrapper4 + QP_Wrapper; Pinocchio / "
