@@ -45,7 +45,7 @@ def test_header_is_plain_c_and_ctypes_layout_matches(tmp_path):
     """Compile the header as C (gcc, no CUDA, no torch types) and compare sizeof / offsetof with the ctypes mirrors."""
     from wbc_b200 import _cabi
     structs = {"WbcTreeTable": _cabi.WbcTreeTable, "WbcConfig": _cabi.WbcConfig, "WbcStepIO": _cabi.WbcStepIO,
-               "WbcAssembleOut": _cabi.WbcAssembleOut}
+               "WbcAssembleOut": _cabi.WbcAssembleOut, "WbcHostIO": _cabi.WbcHostIO}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for sname, cls in structs.items():
         lines.append(f'  printf("{sname} %zu\\n", sizeof({sname}));')
