@@ -157,6 +157,10 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
   double u = 0.0, rinv = 0.0;
   int bstat = 0, cstat = 0;                  // 0 none 1 lower 2 upper 3 eq
   bool fixed = false;
+  // RED: the (at most four) rows of C that are not foot rows keep their d vectors as extra "rows of J" in the spare lanes
+  // [NV, NV + 4): row c sits in lane hl_mine of lane c (-1: none), so the second array Dr and its passes vanish
+  int hl_mine = -1;
+  unsigned other_rows = 0;
 #include "wbc_qp_red.inc"
   if (!RED) {
   if (NF > 0) {                              // g_i += sum_k H[i][k] x_k over the statically fixed variables
@@ -586,6 +590,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
     // broadcast the (unsigned) d vector of the entering constraint; keep d_lane, then zero the first iq entries
     if (is_box) {
       if (lane == owner) publish_row<NQ, P0>(vd_a, Jr);
+    } else if (RED) {
+      if (lane == NV + __popc(other_rows & ((1u << owner) - 1u))) publish_row<NQ, P0>(vd_a, Jr);
     } else {
       if (crow == owner) publish_row<ND>(vd_a + doff, Dr);         // SPLIT: both halves write their segment
     }
@@ -610,7 +616,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
         if (!SPLIT) w1 = fma(Dr[WBC_DX(2 * p + 1)], d2.y, w1);
       }
     }
-    if (SPLIT) {
+    if (SPLIT && !RED) {
 #pragma unroll
       for (int p = 0; p < ND / 2; ++p) {
         const double2 d2 = lds_f64x2(vd_a + doff + 16 * p);
@@ -619,8 +625,12 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
       }
     }
     double w = w0 + w1;
-    if (SPLIT) w += __shfl_xor_sync(WBC_FULL_MASK, w, 16);
+    if (SPLIT && !RED) w += __shfl_xor_sync(WBC_FULL_MASK, w, 16);
     const double z = z0 + z1, dd2 = e0 + e1;
+    if (RED) {                                                     // C_c z is the z of the lane that carries row c
+      const double zr = __shfl_sync(WBC_FULL_MASK, z, hl_mine >= 0 ? hl_mine : 0);
+      w = (hl_mine >= 0) ? zr : 0.0;
+    }
     // r = R^-1 d1 on the inequality block [p_eq, iq)
     double rr = (lane < iq) ? sgn * d_own : 0.0;
 #pragma unroll 1
@@ -696,7 +706,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
 #define WBC_GV(j) case (j): if ((j) >= P0 && (j) + 1 < NQ) { \
               const double j0 = Jr[WBC_IX(j)], j1 = Jr[WBC_IX((j) + 1)]; \
               Jr[WBC_IX(j)] = cg * j0 + sg * j1; Jr[WBC_IX((j) + 1)] = -sg * j0 + cg * j1; \
-              if (!SPLIT || (j) + 1 < HALF) { \
+              if (RED) { \
+              } else if (!SPLIT || (j) + 1 < HALF) { \
                 if (!upper) { const double d0 = Dr[WBC_DX(j)], d1 = Dr[WBC_DX((j) + 1)]; \
                   Dr[WBC_DX(j)] = cg * d0 + sg * d1; Dr[WBC_DX((j) + 1)] = -sg * d0 + cg * d1; } \
               } else if ((j) >= HALF) { \
@@ -740,14 +751,15 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
       double jiq = 0.0, diq = 0.0;
       switch (iq) {                                                   // column iq of J and of the rows' d vectors
 #define WBC_PK(j) case (j): if ((j) >= P0 && (j) < NQ) { jiq = Jr[WBC_IX(j)]; \
-          if (!SPLIT) diq = Dr[WBC_DX(j)]; \
+          if (RED) { } \
+          else if (!SPLIT) diq = Dr[WBC_DX(j)]; \
           else if ((j) < HALF) diq = upper ? 0.0 : Dr[WBC_DX(j)]; \
           else diq = upper ? Dr[WBC_DX((j) - HALF)] : 0.0; } break;
         WBC_REP32_ASC(WBC_PK)
 #undef WBC_PK
         default: break;
       }
-      if (SPLIT) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
+      if (SPLIT && !RED) diq += __shfl_xor_sync(WBC_FULL_MASK, diq, 16);
       const double nbJ = -beta * fma(sigma, jiq, z);
       const double nbD = -beta * fma(sigma, diq, w);
       sts_f64_if(lane == 0, vd_a + 8 * iq, v_iq);                    // vd = v = d2 + sigma e_iq (zeros below iq)
@@ -764,7 +776,7 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
           if (!SPLIT) Dr[WBC_DX(2 * p + 1)] = fma(nbD, v2.y, Dr[WBC_DX(2 * p + 1)]);
         }
       }
-      if (SPLIT) {
+      if (SPLIT && !RED) {
 #pragma unroll
         for (int p = 0; p < ND / 2; ++p) {
           const double2 v2 = lds_f64x2(vd_a + doff + 16 * p);
