@@ -11,7 +11,9 @@
  *   - every array pointer is a BORROWED DEVICE pointer (row-major, float64 unless noted);
  *     NULL means "not requested" for optional outputs.  Nothing is allocated inside the calls.
  *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it.
- *   - a WbcModel is immutable after creation and may be shared by streams/threads.
+ *   - a WbcModel is immutable after creation and may be shared by streams/threads (wbc_step_host excepted: it owns
+ *     a copy / compute pipeline inside the handle).  It lives on the CUDA device that was current when it was created;
+ *     every later call must be made with that device current (WBC_ERR_INVALID_ARG otherwise).
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
  *
  * Batched layout (N = number of robot states, leading dimension of every tensor):
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define WBC_ABI_VERSION 1
+#define WBC_ABI_VERSION 2
 
 #define WBC_MAX_JOINTS 32
 #define WBC_MAX_NV 32
@@ -40,7 +42,7 @@ extern "C" {
 #define WBC_NUM_EE 5
 #define WBC_FRAME_TRUNK 5      /* frame slots 0..4 = EE frames FR FL RR RL GRIP, slot 5 = trunk (imu) frame */
 #define WBC_MAX_NC 32          /* rows of C handled by the QP kernels */
-#define WBC_MAX_EXTRA_ROWS 16  /* extension rows (friction pyramid / torque proxy); not in the reference */
+#define WBC_MAX_EXTRA_ROWS 24  /* extension rows (friction pyramid / torque proxy); not in the reference */
 
 #define WBC_TARGETS_STRIDE 18
 #define WBC_MEM_STRIDE 72
@@ -171,6 +173,8 @@ typedef struct WbcStepIO {
   uint64_t* active_set;     /* [N, 2] or NULL: word0 = box bounds (bit 2k lower, 2k+1 upper of x_k), word1 = rows of C */
   double* mem_out;          /* [N, 72] or NULL: task memory after the tick (may alias mem_in) */
   double* q_next;           /* [N, nq] or NULL: integrate + base estimate (:1397-1402, :1297-1327); may alias q */
+  double* joint_targets;    /* [N, nq - 7] or NULL: q_next[7:], the joint position targets runWBC returns as its five
+                               slices FL, FR, RL, RR, grip (:1405-1412); needs q_next */
 } WbcStepIO;
 
 /* Accessor / debug outputs of the assembly stage: what qpA, qpb, velDamperJointConstraints and
@@ -215,6 +219,13 @@ int wbc_init_memory(const WbcModel* model, const double* q, int64_t N, double* m
 int wbc_integrate(const WbcModel* model, const double* q, const double* v, int64_t N, double scale, double* q_out,
                   void* stream);
 
+/* updateState(joint_config, imu_data, running=True) (Robot_Wrapper4.py:387-428) without the accessor refresh: the base
+ * orientation of q is replaced by imu_quat (NULL: kept), FK, trunkWorldPos (:1297-1327: base xyz re-estimated from the
+ * four foot targets, targets [N, 18] as in WbcStepIO), and q_out = [estimated xyz, quaternion, joints].  base_out [N, 3]
+ * (or NULL) receives just the estimate, i.e. what trunkWorldPos() returns.  q_out may be NULL or alias q. */
+int wbc_base_estimate(const WbcModel* model, const double* q, const double* imu_quat, const double* targets, int64_t N,
+                      double* q_out, double* base_out, void* stream);
+
 /* qpA / qpb / velDamperJointConstraints / findConstraints (+ H, g) without solving. */
 int wbc_assemble(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, int64_t N,
                  const WbcAssembleOut* out, void* stream);
@@ -230,30 +241,52 @@ int wbc_qp_solve(int64_t N, int32_t nv, int32_t m, int32_t nC, const double* A, 
 /* the fused tick */
 int wbc_step(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, int64_t N, void* stream);
 
+/* element type of the floating-point HOST arrays of wbc_step_host */
+#define WBC_HOST_F64 0
+#define WBC_HOST_F32 1         /* optional FP32 I/O mode: float32 arrays on the host side (half the PCIe bytes); the tick
+                                  itself still computes in float64.  Agreement with the float64 call: <= 1e-4 */
+
+/* WbcHostIO.flags.  DELTA_INPUTS (float32, closed loop only): `targets` holds the INCREMENT of every target over the
+ * previous tick's target (the task memory's prev_EE_pos / prev_trunk_ref, Robot_Wrapper4.py:995, :1151) and `imu_quat`
+ * the increment of the base quaternion over the resident q[3:7]; the tick adds them back in float64.  A float32
+ * increment of ~1e-3 carries an absolute error of ~1e-10, a float32 position of ~0.5 m one of ~3e-8 -- which the target
+ * laws multiply by 1 / dt = 500.  With increments the FP32 I/O mode agrees with the float64 call to < 1e-4 in qdot;
+ * with absolute float32 targets only the joint position targets do (qdot: ~1e-5 typical, ~3e-3 worst case). */
+#define WBC_HOST_FLAG_DELTA_INPUTS 1
+
 /* Host-side arrays of one tick for wbc_step_host: what a caller of the reference holds as NumPy arrays
  * (runWBC's arguments and return values, Robot_Wrapper4.py:1330-1412).  Page-locked memory makes the copies
  * asynchronous; pageable memory works but serialises them.  An input left NULL is not copied: it is resident in the
- * device buffer of `io` already (e.g. the task memory and per-robot references, which the reference keeps as
- * attributes of the controller object).  An output left NULL is not copied back. */
+ * device buffer of `io` already (the configuration, the task memory and the per-robot references, which the reference
+ * keeps as attributes of the controller object).  An output left NULL is not copied back. */
 typedef struct WbcHostIO {
-  const double* q;          /* [N, nq] */
-  const double* targets;    /* [N, 18] */
-  const double* mem_in;     /* [N, 72] or NULL */
-  const double* ref;        /* [N, 24] or NULL */
-  double* qdot;             /* [N, nv] */
-  int32_t* status;          /* [N] */
-  int32_t* iters;           /* [N] */
+  const void* q;            /* [N, nq] or NULL */
+  const void* targets;      /* [N, 18] */
+  const void* mem_in;       /* [N, 72] or NULL */
+  const void* ref;          /* [N, 24] or NULL */
+  const void* imu_quat;     /* [N, 4] or NULL: runWBC's base_config (:1330, :1402); needs io->q_next */
+  void* qdot;               /* [N, nv] or NULL */
+  int32_t* status;          /* [N] or NULL */
+  int32_t* iters;           /* [N] or NULL */
+  void* joint_targets;      /* [N, nq - 7] or NULL: what runWBC returns (:1405-1412); needs io->q_next */
+  int32_t dtype;            /* WBC_HOST_F64 / WBC_HOST_F32: element type of q, targets, mem_in, ref, imu_quat, qdot, joint_targets */
+  int32_t flags;            /* WBC_HOST_FLAG_* */
 } WbcHostIO;
 
-/* The open-loop tick with host buffers.  `io` names the device buffers (all of wbc_step's required members;
- * q_next / mem_out / imu_quat / active_set must be NULL); those of the travelling members are staging space whose
- * contents are unspecified afterwards.
+/* One tick with host buffers: runWBC as its callers see it (NumPy arrays in, NumPy arrays out).  `io` names the device
+ * buffers: all of wbc_step's required members; for every travelling array its device twin is staging space whose
+ * contents are unspecified afterwards (io->imu_quat / io->joint_targets are needed as staging only when chunks >= 1).
+ *   open loop    io->q_next == NULL, io->mem_out == NULL: nothing on the device is advanced;
+ *   closed loop  io->q_next == io->q and io->mem_out == io->mem_in (both resident: host->q and host->mem_in NULL): the
+ *                configuration and the task memory are advanced in place exactly as runWBC mutates its object
+ *                (:995-996, :1151-1152, :1397-1402); per tick only the IMU quaternion and the targets travel in and the
+ *                joint targets / status out.  K calls equal wbc_rollout over the same K ticks.
  *   chunks <= 0  automatic: if every host array is page-locked the kernel reads the inputs from and writes the outputs
  *                to host memory directly (zero-copy, one launch on `stream`); otherwise as chunks = 8;
  *   chunks >= 1  staged: the batch is cut into `chunks` wave-aligned slices whose host->device copies, kernel and
  *                device->host copies overlap on three streams owned by the model (created on first use).
- * Asynchronous: `stream` is ordered before the first access and after the last; synchronise it before reading the host
- * outputs.  Not re-entrant per model handle. */
+ * io->active_set must be NULL.  Asynchronous: `stream` is ordered before the first access and after the last;
+ * synchronise it before reading the host outputs.  Not re-entrant per model handle. */
 int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const WbcHostIO* host, int64_t N,
                   int32_t chunks, void* stream);
 

@@ -11,11 +11,11 @@ The directory name contains hyphens, so import it through the ``wbc_b200`` shim 
 from . import _cabi
 from ._cabi import WbcError, build_library, load as load_library
 from .tree_table import TreeTable
-from .robot_model import RobotModel, LinearTrajectory, EE_FRAME_NAMES, EE_JOINT_NAMES, HIP_WAIST_JOINT_NAMES
+from .robot_model import RobotModel, LinearTrajectory, HostDeltaEncoder, EE_FRAME_NAMES, EE_JOINT_NAMES, HIP_WAIST_JOINT_NAMES
 from .qp import QP
 from . import synthetic
 from . import sharding
 from . import mocap
 
-__all__ = ["RobotModel", "LinearTrajectory", "mocap", "QP", "TreeTable", "WbcError", "build_library", "load_library", "synthetic", "sharding",
+__all__ = ["RobotModel", "LinearTrajectory", "HostDeltaEncoder", "mocap", "QP", "TreeTable", "WbcError", "build_library", "load_library", "synthetic", "sharding",
            "EE_FRAME_NAMES", "EE_JOINT_NAMES", "HIP_WAIST_JOINT_NAMES"]

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("WBC_B200_LIB") or os.path.join(PKG_DIR, "libwbc_b200.so")   # override: A/B builds only
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "wbc_b200.h")
 
-MAX_JOINTS, MAX_NV, MAX_NQ, MAX_FRAMES, NUM_EE, MAX_NC, MAX_EXTRA = 32, 32, 33, 16, 5, 32, 16
+MAX_JOINTS, MAX_NV, MAX_NQ, MAX_FRAMES, NUM_EE, MAX_NC, MAX_EXTRA = 32, 32, 33, 16, 5, 32, 24
 FRAME_TRUNK = 5
 TARGETS_STRIDE, MEM_STRIDE, REF_STRIDE = 18, 72, 24
 RF_WORLD, RF_LOCAL, RF_LOCAL_WORLD_ALIGNED = 0, 1, 2
@@ -26,12 +26,16 @@ CON_COM, CON_TRUNK, CON_FR, CON_FL, CON_RR, CON_RL, CON_GRIP = 1, 2, 4, 8, 16, 3
 COMPAT_DAMPER_OFF_BY_ONE = 1
 QP_SOLVED, QP_MAXITER, QP_INFEASIBLE, QP_NOT_PD = 0, 1, 2, 4
 STEP_FLAG_PLAIN_INTEGRATE = 1
+HOST_F64, HOST_F32 = 0, 1
+HOST_FLAG_DELTA_INPUTS = 1
+ABI_VERSION = 2
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 JT_UNIVERSE, JT_FREEFLYER, JT_REVOLUTE, JT_PRISMATIC = 0, 1, 2, 3
 
 EXPORTS = [
     "wbc_abi_version", "wbc_last_error", "wbc_model_create", "wbc_model_destroy", "wbc_config_rows",
-    "wbc_fk_jac", "wbc_joint_jacobians", "wbc_init_memory", "wbc_integrate", "wbc_assemble", "wbc_qp_solve", "wbc_step",
+    "wbc_fk_jac", "wbc_joint_jacobians", "wbc_init_memory", "wbc_integrate", "wbc_base_estimate", "wbc_assemble",
+    "wbc_qp_solve", "wbc_step",
     "wbc_rollout", "wbc_step_host",
     "wbc_step_launch_info", "wbc_measure_fp64_peak",
 ]
@@ -71,13 +75,14 @@ class WbcStepIO(C.Structure):
         ("q", C.c_void_p), ("targets", C.c_void_p), ("mem_in", C.c_void_p), ("ref", C.c_void_p),
         ("imu_quat", C.c_void_p), ("dt", f64), ("flags", C.c_int64),
         ("qdot", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p), ("active_set", C.c_void_p),
-        ("mem_out", C.c_void_p), ("q_next", C.c_void_p),
+        ("mem_out", C.c_void_p), ("q_next", C.c_void_p), ("joint_targets", C.c_void_p),
     ]
 
 
 class WbcHostIO(C.Structure):
     _fields_ = [("q", C.c_void_p), ("targets", C.c_void_p), ("mem_in", C.c_void_p), ("ref", C.c_void_p),
-                ("qdot", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p)]
+                ("imu_quat", C.c_void_p), ("qdot", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p),
+                ("joint_targets", C.c_void_p), ("dtype", i32), ("flags", i32)]
 
 
 class WbcAssembleOut(C.Structure):
@@ -130,6 +135,7 @@ def load():
     lib.wbc_joint_jacobians.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.wbc_init_memory.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.wbc_integrate.argtypes = [vp, vp, vp, i64, f64, vp, vp]
+    lib.wbc_base_estimate.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp]
     lib.wbc_assemble.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), i64, C.POINTER(WbcAssembleOut), vp]
     lib.wbc_qp_solve.argtypes = [i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wbc_step.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), i64, vp]
@@ -140,7 +146,7 @@ def load():
     for name in EXPORTS:
         if name not in ("wbc_last_error", "wbc_model_destroy"):
             getattr(lib, name).restype = C.c_int
-    if lib.wbc_abi_version() != 1:
+    if lib.wbc_abi_version() != ABI_VERSION:
         raise WbcError("libwbc_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -255,10 +255,56 @@ __global__ void __launch_bounds__(256) wbc_init_memory_kernel(const DevModel* __
   }
 }
 
+// updateState(..., running=True) minus the accessor refresh (Robot_Wrapper4.py:387-428): IMU quaternion into q, FK,
+// trunkWorldPos (:1297-1327), q_out = [estimated base xyz, quaternion, joints].  One state per warp.
+__global__ void __launch_bounds__(256) wbc_base_estimate_kernel(const DevModel* __restrict__ model, const double* q,
+                                                                const double* __restrict__ imu, const double* __restrict__ targets,
+                                                                long long N, double* q_out, double* __restrict__ base_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
+  stage_model(model, Ms);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int per_warp = WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40;
+  double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * per_warp;
+  double* oMi = ws;
+  double* oMf = ws + WBC_MAX_JOINTS * WBC_T_STRIDE;
+  double* qs = oMf + WBC_MAX_FRAMES * WBC_T_STRIDE;
+  const int nq = Ms->nq;
+  for (long long s = (long long)blockIdx.x * wpc + warp; s < N; s += (long long)gridDim.x * wpc) {
+    for (int i = lane; i < nq; i += 32) qs[i] = (imu && i >= 3 && i < 7) ? imu[s * 4 + (i - 3)] : q[s * nq + i];
+    __syncwarp();
+    warp_fk(Ms, qs, oMi, lane);
+    warp_frames(Ms, oMi, oMf, lane);
+    if (lane == 0) {
+      const double* Tt = oMf + WBC_FRAME_TRUNK * WBC_T_STRIDE;
+      const double* tg = targets + s * WBC_TARGETS_STRIDE;
+      double BPA[3], WPA[3], rb[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {            // sums in the reference's order: FR + FL + RR + RL
+        const double d0 = oMf[0 * WBC_T_STRIDE + 9 + c] - Tt[9 + c], d1 = oMf[1 * WBC_T_STRIDE + 9 + c] - Tt[9 + c];
+        const double d2 = oMf[2 * WBC_T_STRIDE + 9 + c] - Tt[9 + c], d3 = oMf[3 * WBC_T_STRIDE + 9 + c] - Tt[9 + c];
+        BPA[c] = (d0 + d1 + d2 + d3) / 4;
+        WPA[c] = (tg[c] + tg[3 + c] + tg[6 + c] + tg[9 + c]) / 4;
+      }
+      mat3_vec(Tt, BPA, rb);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        qs[c] = WPA[c] - rb[c];
+        if (base_out) base_out[s * 3 + c] = qs[c];
+      }
+    }
+    __syncwarp();
+    if (q_out)
+      for (int i = lane; i < nq; i += 32) q_out[s * nq + i] = qs[i];
+    __syncwarp();
+  }
+}
+
 // pin.integrate(model, q, v)  (jointVelocitiestoConfig, Robot_Wrapper4.py:440-441): one state per warp
-__global__ void __launch_bounds__(256) wbc_integrate_kernel(const DevModel* __restrict__ model, const double* __restrict__ q,
+// (q and out may alias -- wbc_b200.h allows q_out == q -- so neither is __restrict__)
+__global__ void __launch_bounds__(256) wbc_integrate_kernel(const DevModel* __restrict__ model, const double* q,
                                                             const double* __restrict__ v, long long N, double scale,
-                                                            double* __restrict__ out) {
+                                                            double* out) {
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -519,6 +565,15 @@ static int build_dev_model(const WbcTreeTable* t, DevModel* m) {
   return WBC_OK;
 }
 
+// Every entry point launches with the model's device pointers: the caller's current device must be the one the model
+// was created on (wbc_b200.h).
+static int check_device(const WbcModel* model) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != model->device)
+    return fail(WBC_ERR_INVALID_ARG, "the model was created on another CUDA device than the current one%s");
+  return WBC_OK;
+}
+
 static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15); }
 
 template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0, bool RED = false>
@@ -620,11 +675,23 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   if (cfg->n_extra_rows < 0 || cfg->n_extra_rows > WBC_MAX_EXTRA_ROWS) return fail(WBC_ERR_INVALID_ARG, "n_extra_rows out of range%s");
   for (int e = 0; e < cfg->n_extra_rows; ++e)
     if (cfg->extra_frame[e] < 0 || cfg->extra_frame[e] >= WBC_HOT_FRAMES) return fail(WBC_ERR_INVALID_ARG, "extra row frame must be a hot frame slot 0..5%s");
+  for (int e = 0; e < cfg->n_extra_rows; ++e)
+    if (cfg->extra_rf[e] < WBC_RF_WORLD || cfg->extra_rf[e] > WBC_RF_LOCAL_WORLD_ALIGNED)
+      return fail(WBC_ERR_INVALID_ARG, "extra row reference frame must be WORLD, LOCAL or LOCAL_WORLD_ALIGNED%s");
   if (!(cfg->task_mask & 0x7f)) return fail(WBC_ERR_INVALID_ARG, "no task selected%s");
+  // end_effector_index_list_joint[4]: a joint id, or njoints when the model has no such joint (pin.getJointId's answer
+  // for an unknown name: nothing gets locked, laikago_vx300)
+  if (cfg->gripper_joint_id < 2 || cfg->gripper_joint_id > model->host.njoints)
+    return fail(WBC_ERR_INVALID_ARG, "gripper_joint_id must be in [2, njoints]%s");
+  if ((cfg->task_mask & WBC_TASK_JOINT) && cfg->joint_mode == WBC_JOINT_HYBRID &&
+      (cfg->arm_base_id < 1 || cfg->arm_base_id >= model->host.njoints))
+    return fail(WBC_ERR_INVALID_ARG, "arm_base_id must be a joint id in [1, njoints) for the HYBRID joint task%s");
   if (!io->q || !io->targets || !io->mem_in || !io->ref) return fail(WBC_ERR_INVALID_ARG, "q / targets / mem_in / ref are required%s");
   if (!(io->dt > 0.0)) return fail(WBC_ERR_INVALID_ARG, "dt must be positive%s");
+  if (int rc = check_device(model)) return rc;
   P->model = model->dev;
   P->cfg = *cfg;
+  if (P->cfg.max_iter <= 0) P->cfg.max_iter = 200;           // same default as wbc_qp_solve
   P->io = *io;
   memset(&P->dbg, 0, sizeof(P->dbg));
   P->nC = cfg_nc(*cfg);
@@ -642,6 +709,8 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   }
   if (P->nC > WBC_MAX_NC) return fail(WBC_ERR_UNSUPPORTED, "more than 32 constraint rows%s");
   P->grid_cap = 0;
+  P->f32_in = P->f32_out = 0;
+  if (io->joint_targets && !io->q_next) return fail(WBC_ERR_INVALID_ARG, "joint_targets needs q_next%s");
   set_reduced(model->host, P);
   return WBC_OK;
 }
@@ -692,6 +761,7 @@ int wbc_config_rows(const WbcConfig* cfg, int32_t nv, int32_t* m_rows, int32_t* 
 }
 
 static int fk_common(const WbcModel* model, FkJacParams& P, void* stream) {
+  if (int rc = check_device(model)) return rc;
   const int wpc = 8;
   const size_t per_warp = (WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40) * sizeof(double);
   const size_t smem = model_smem_bytes() + wpc * per_warp;
@@ -732,6 +802,7 @@ int wbc_joint_jacobians(const WbcModel* model, const double* q, int64_t N, doubl
 
 int wbc_init_memory(const WbcModel* model, const double* q, int64_t N, double* mem_out, double* ref_out, void* stream) {
   if (!model || !q || !mem_out || !ref_out || N < 0) return fail(WBC_ERR_INVALID_ARG, "null argument or negative N%s");
+  if (int rc = check_device(model)) return rc;
   const int wpc = 8;
   const size_t per_warp = (WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40) * sizeof(double);
   const size_t smem = model_smem_bytes() + wpc * per_warp;
@@ -747,10 +818,29 @@ int wbc_init_memory(const WbcModel* model, const double* q, int64_t N, double* m
 int wbc_integrate(const WbcModel* model, const double* q, const double* v, int64_t N, double scale, double* q_out,
                   void* stream) {
   if (!model || !q || !v || !q_out || N < 0) return fail(WBC_ERR_INVALID_ARG, "null argument or negative N%s");
+  if (int rc = check_device(model)) return rc;
   if (N == 0) return WBC_OK;
   long long need = (N + 7) / 8;
   const long long cap = (long long)model->sm_count * 8;
   wbc_integrate_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(model->dev, q, v, N, scale, q_out);
+  CUDA_TRY(cudaGetLastError());
+  return WBC_OK;
+}
+
+int wbc_base_estimate(const WbcModel* model, const double* q, const double* imu_quat, const double* targets, int64_t N,
+                      double* q_out, double* base_out, void* stream) {
+  if (!model || !q || !targets || N < 0) return fail(WBC_ERR_INVALID_ARG, "null model / q / targets or negative N%s");
+  if (!q_out && !base_out) return fail(WBC_ERR_INVALID_ARG, "no output requested%s");
+  if (int rc = check_device(model)) return rc;
+  const int wpc = 8;
+  const size_t per_warp = (WBC_MAX_JOINTS * WBC_T_STRIDE + WBC_MAX_FRAMES * WBC_T_STRIDE + 40) * sizeof(double);
+  const size_t smem = model_smem_bytes() + wpc * per_warp;
+  CUDA_TRY(cudaFuncSetAttribute(wbc_base_estimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (N == 0) return WBC_OK;
+  long long need = (N + wpc - 1) / wpc;
+  const long long cap = (long long)model->sm_count * 4;
+  wbc_base_estimate_kernel<<<(int)(need < cap ? need : cap), wpc * 32, smem, (cudaStream_t)stream>>>(model->dev, q, imu_quat, targets, N,
+                                                                                                q_out, base_out);
   CUDA_TRY(cudaGetLastError());
   return WBC_OK;
 }
@@ -776,9 +866,9 @@ int wbc_step(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, i
 }
 
 // The fused tick for a caller that holds host arrays (the reference's calling convention: NumPy in, NumPy out,
-// Robot_Wrapper4.py:1330-1412).  The batch is cut into `chunks` slices; host -> device copies, the kernel and the
-// device -> host copies of consecutive slices overlap on three internal streams.  `stream` is ordered before the first
-// copy and after the last one.
+// Robot_Wrapper4.py:1330-1412).  Zero-copy (page-locked arrays: the kernel reads / writes them over PCIe itself) or
+// staged (the batch cut into `chunks` slices whose host -> device copies, kernel and device -> host copies overlap on
+// three internal streams).  `stream` is ordered before the first access and after the last one.
 int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const WbcHostIO* host, int64_t N,
                   int32_t chunks, void* stream) {
   StepParams P;
@@ -786,37 +876,66 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
   if (rc != WBC_OK) return rc;
   if (!host) return fail(WBC_ERR_INVALID_ARG, "null host io%s");
   if (N < 0 || !io->qdot || !io->status || !io->iters) return fail(WBC_ERR_INVALID_ARG, "qdot / status / iters are required%s");
-  if (io->q_next || io->mem_out || io->imu_quat || io->active_set)
-    return fail(WBC_ERR_UNSUPPORTED, "wbc_step_host runs the open-loop tick (q_next / mem_out / imu_quat / active_set must be NULL)%s");
+  if (io->active_set) return fail(WBC_ERR_UNSUPPORTED, "wbc_step_host does not report active sets (io->active_set must be NULL)%s");
+  if (host->dtype != WBC_HOST_F64 && host->dtype != WBC_HOST_F32) return fail(WBC_ERR_INVALID_ARG, "unknown host dtype%s");
+  if (!host->targets) return fail(WBC_ERR_INVALID_ARG, "host targets are required (they are runWBC's arguments)%s");
+  // closed loop: the configuration and the task memory are advanced in place on the device, as runWBC mutates its object
+  if (io->q_next && (io->q_next != io->q || host->q))
+    return fail(WBC_ERR_INVALID_ARG, "closed loop: q_next must alias the resident q (host q NULL)%s");
+  if (io->mem_out && (io->mem_out != io->mem_in || host->mem_in))
+    return fail(WBC_ERR_INVALID_ARG, "closed loop: mem_out must alias the resident mem_in (host mem_in NULL)%s");
+  if ((host->imu_quat || host->joint_targets) && !io->q_next)
+    return fail(WBC_ERR_INVALID_ARG, "imu_quat / joint_targets belong to the closed-loop tick (io->q_next)%s");
   if (N == 0) return WBC_OK;
+  const bool f32 = host->dtype == WBC_HOST_F32;
+  const int nq = model->host.nq, nv = model->host.nv;
+  // the seven travelling arrays: host pointer, device twin, elements per state, FP32 flag bit, direction
+  struct Arr { const void* h; const void** d; int n; int bit; bool out; bool flt; };
+  Arr arr[9] = {
+      {host->q, (const void**)&P.io.q, nq, WBC_F32_Q, false, true},
+      {host->targets, (const void**)&P.io.targets, WBC_TARGETS_STRIDE, WBC_F32_TARGETS, false, true},
+      {host->mem_in, (const void**)&P.io.mem_in, WBC_MEM_STRIDE, WBC_F32_MEM, false, true},
+      {host->ref, (const void**)&P.io.ref, WBC_REF_STRIDE, WBC_F32_REF, false, true},
+      {host->imu_quat, (const void**)&P.io.imu_quat, 4, WBC_F32_IMU, false, true},
+      {host->qdot, (const void**)&P.io.qdot, nv, WBC_F32_QDOT, true, true},
+      {host->joint_targets, (const void**)&P.io.joint_targets, nq - 7, WBC_F32_JOINTS, true, true},
+      {host->status, (const void**)&P.io.status, 1, 0, true, false},
+      {host->iters, (const void**)&P.io.iters, 1, 0, true, false}};
+  P.f32_in = P.f32_out = 0;
+  if (f32)
+    for (int k = 0; k < 7; ++k)
+      if (arr[k].h) (arr[k].out ? P.f32_out : P.f32_in) |= arr[k].bit;
+  if (host->flags & WBC_HOST_FLAG_DELTA_INPUTS) {
+    if (!f32 || !io->q_next || !io->mem_out || host->mem_in || host->q)
+      return fail(WBC_ERR_INVALID_ARG, "increment inputs need float32 host arrays and the closed-loop tick (resident q / task memory)%s");
+    P.f32_in |= WBC_F32_DELTA;
+  }
   if (chunks <= 0) {
     // Zero-copy: when every host array is page-locked (and therefore mapped into the device's address space under
-    // unified addressing) the kernel reads q / targets straight from host memory -- its cp.async prefetch runs a whole tick
-    // ahead, which hides the PCIe latency -- and writes qdot / status / iters straight into host memory: one launch, no
-    // staging copies, no per-slice ramp-up / ramp-down.  Measured: 91 M steps/s against 82 M for the sliced pipeline.
-    struct { const void* h; const void** d; } m[7] = {
-        {host->q, (const void**)&P.io.q}, {host->targets, (const void**)&P.io.targets},
-        {host->mem_in, (const void**)&P.io.mem_in}, {host->ref, (const void**)&P.io.ref},
-        {host->qdot, (const void**)&P.io.qdot}, {host->status, (const void**)&P.io.status},
-        {host->iters, (const void**)&P.io.iters}};
+    // unified addressing) the kernel reads the inputs straight from host memory -- its cp.async prefetch runs a whole tick
+    // ahead, which hides the PCIe latency -- and writes the outputs straight into host memory: one launch, no staging
+    // copies, no per-slice ramp-up / ramp-down.
     bool mapped = true;
-    const void* dptr[7];
-    for (int k = 0; k < 7 && mapped; ++k) {
+    const void* dptr[9];
+    for (int k = 0; k < 9 && mapped; ++k) {
       dptr[k] = nullptr;
-      if (!m[k].h) continue;
+      if (!arr[k].h) continue;
       cudaPointerAttributes a;
-      if (cudaPointerGetAttributes(&a, m[k].h) != cudaSuccess) { cudaGetLastError(); mapped = false; break; }
+      if (cudaPointerGetAttributes(&a, arr[k].h) != cudaSuccess) { cudaGetLastError(); mapped = false; break; }
       if (a.type != cudaMemoryTypeHost || !a.devicePointer) mapped = false;
       else dptr[k] = a.devicePointer;
     }
     if (mapped) {
-      for (int k = 0; k < 7; ++k)
-        if (m[k].h) *m[k].d = dptr[k];
+      for (int k = 0; k < 9; ++k)
+        if (arr[k].h) *arr[k].d = dptr[k];
       P.N = N;
       return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
     }
     chunks = 8;                            // pageable host memory: staged copies
   }
+  // staged: the device twins of the travelling arrays are the staging space
+  if (host->imu_quat && !io->imu_quat) return fail(WBC_ERR_INVALID_ARG, "staged copies: io->imu_quat is needed as staging space%s");
+  if (host->joint_targets && !io->joint_targets) return fail(WBC_ERR_INVALID_ARG, "staged copies: io->joint_targets is needed as staging space%s");
   if (!model->pipe_ready) {
     for (int s = 0; s < WBC_PIPE_STREAMS; ++s) {
       CUDA_TRY(cudaStreamCreateWithFlags(&model->pipe[s], cudaStreamNonBlocking));
@@ -851,38 +970,44 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
     }
   }
   const cudaStream_t user = (cudaStream_t)stream;
-  const int nq = model->host.nq, nv = model->host.nv;
-  CUDA_TRY(cudaEventRecord(model->pipe_start, user));
-  for (int c = 0; c < chunks; ++c) {
-    const int64_t lo = bnd[c], hi = bnd[c + 1], n = hi - lo;
+  const size_t fsz = f32 ? sizeof(float) : sizeof(double);
+  const void* dev0[9];                       // device twins at state 0
+  for (int k = 0; k < 9; ++k) dev0[k] = *arr[k].d;
+  // any failure inside the slice loop still joins the internal streams back into the caller's stream before returning:
+  // copies / kernels already queued must not outlive the call unobserved (the caller may free or reuse its buffers)
+  cudaError_t ce = cudaEventRecord(model->pipe_start, user);
+  int used = 0;
+  for (int c = 0; c < chunks && ce == cudaSuccess && rc == WBC_OK; ++c) {
+    const int64_t lo = bnd[c], n = bnd[c + 1] - lo;
     if (n <= 0) continue;
     const cudaStream_t st = model->pipe[c % WBC_PIPE_STREAMS];
-    if (c < WBC_PIPE_STREAMS) CUDA_TRY(cudaStreamWaitEvent(st, model->pipe_start, 0));
-    struct { const double* h; const double* d; int stride; } in[4] = {
-        {host->q, io->q, nq}, {host->targets, io->targets, WBC_TARGETS_STRIDE},
-        {host->mem_in, io->mem_in, WBC_MEM_STRIDE}, {host->ref, io->ref, WBC_REF_STRIDE}};
-    for (int k = 0; k < 4; ++k)
-      if (in[k].h)                       // NULL: resident on the device already
-        CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(in[k].d) + lo * in[k].stride, in[k].h + lo * in[k].stride,
-                                 sizeof(double) * n * in[k].stride, cudaMemcpyHostToDevice, st));
-    P.io.q = io->q + lo * nq;
-    P.io.targets = io->targets + lo * WBC_TARGETS_STRIDE;
-    P.io.mem_in = io->mem_in + lo * WBC_MEM_STRIDE;
-    P.io.ref = io->ref + lo * WBC_REF_STRIDE;
-    P.io.qdot = io->qdot + lo * nv;
-    P.io.status = io->status + lo;
-    P.io.iters = io->iters + lo;
+    if (c < WBC_PIPE_STREAMS) { ce = cudaStreamWaitEvent(st, model->pipe_start, 0); used = c + 1; }
+    for (int k = 0; k < 9 && ce == cudaSuccess; ++k) {
+      const size_t esz = arr[k].flt ? fsz : sizeof(int32_t);
+      // the kernel's view of this slice: a travelling array is indexed with the host element size, a resident one is float64
+      const size_t step = (size_t)arr[k].n * (arr[k].h ? esz : (arr[k].flt ? sizeof(double) : sizeof(int32_t)));
+      *arr[k].d = dev0[k] ? (const char*)dev0[k] + lo * step : nullptr;
+      if (arr[k].h && !arr[k].out)           // NULL: resident on the device already
+        ce = cudaMemcpyAsync(const_cast<void*>(*arr[k].d), (const char*)arr[k].h + lo * step, n * step, cudaMemcpyHostToDevice, st);
+    }
+    if (ce != cudaSuccess) break;
+    if (io->q_next) P.io.q_next = const_cast<double*>(P.io.q);           // closed loop: in place, slice by slice
+    if (io->mem_out) P.io.mem_out = const_cast<double*>(P.io.mem_in);
     P.N = n;
     rc = launch_step<false>(model, P, st, nullptr);
-    if (rc != WBC_OK) return rc;
-    if (host->qdot) CUDA_TRY(cudaMemcpyAsync(host->qdot + lo * nv, P.io.qdot, sizeof(double) * n * nv, cudaMemcpyDeviceToHost, st));
-    if (host->status) CUDA_TRY(cudaMemcpyAsync(host->status + lo, P.io.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-    if (host->iters) CUDA_TRY(cudaMemcpyAsync(host->iters + lo, P.io.iters, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < 9 && ce == cudaSuccess && rc == WBC_OK; ++k) {
+      if (!arr[k].h || !arr[k].out) continue;
+      const size_t step = (size_t)arr[k].n * (arr[k].flt ? fsz : sizeof(int32_t));
+      ce = cudaMemcpyAsync((char*)const_cast<void*>(arr[k].h) + lo * step, *arr[k].d, n * step, cudaMemcpyDeviceToHost, st);
+    }
   }
-  for (int s = 0; s < WBC_PIPE_STREAMS && s < chunks; ++s) {
-    CUDA_TRY(cudaEventRecord(model->pipe_done[s], model->pipe[s]));
-    CUDA_TRY(cudaStreamWaitEvent(user, model->pipe_done[s], 0));
+  for (int s = 0; s < used; ++s) {
+    cudaError_t e2 = cudaEventRecord(model->pipe_done[s], model->pipe[s]);
+    if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(user, model->pipe_done[s], 0);
+    if (e2 != cudaSuccess) { cudaStreamSynchronize(model->pipe[s]); if (ce == cudaSuccess) ce = e2; }
   }
+  if (rc != WBC_OK) return rc;
+  if (ce != cudaSuccess) return fail(WBC_ERR_CUDA, "wbc_step_host: %s", cudaGetErrorString(ce));
   return WBC_OK;
 }
 
@@ -971,25 +1096,30 @@ int wbc_measure_fp64_peak(double* flops_per_s, void* stream) {
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int blocks = sms * 8, threads = 256, iters = 1 << 16;
   double* buf = nullptr;
-  CUDA_TRY(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
-  wbc_dfma_kernel<<<blocks, threads, 0, st>>>(buf, 1024);           // warm-up
   float best = 1e30f;
-  for (int rep = 0; rep < 3; ++rep) {
-    CUDA_TRY(cudaEventRecord(e0, st));
-    wbc_dfma_kernel<<<blocks, threads, 0, st>>>(buf, iters);
-    CUDA_TRY(cudaEventRecord(e1, st));
-    CUDA_TRY(cudaEventSynchronize(e1));
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    if (ms < best) best = ms;
+  cudaError_t e = cudaMalloc(&buf, sizeof(double) * blocks * threads);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) {
+    wbc_dfma_kernel<<<blocks, threads, 0, st>>>(buf, 1024);           // warm-up
+    e = cudaGetLastError();
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(buf);
+  for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) {
+    e = cudaEventRecord(e0, st);
+    if (e != cudaSuccess) break;
+    wbc_dfma_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    e = cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e == cudaSuccess && ms < best) best = ms;
+  }
+  if (e0) cudaEventDestroy(e0);                                       // one exit: nothing leaks on a failure
+  if (e1) cudaEventDestroy(e1);
+  if (buf) cudaFree(buf);
+  if (e != cudaSuccess) return fail(WBC_ERR_CUDA, "wbc_measure_fp64_peak: %s", cudaGetErrorString(e));
   *flops_per_s = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3);
   return WBC_OK;
 }

@@ -26,6 +26,12 @@
 #include "wbc_device.cuh"
 
 #define WBC_QP_FEAS_TOL 1e-10
+// entering constraint: candidates within TIE_ABS + TIE_REL |min| of the most violated one are tied, the lowest index
+// wins (oracle/qp_wrapper.py).  Mirrored rows (the +-x faces of a friction pyramid once their partners are active) tie
+// exactly in exact arithmetic; without the window rounding noise decides, and the incrementally updated C x of the
+// register solver rounds differently from the fresh products of the oracles.
+#define WBC_QP_TIE_REL 1e-9
+#define WBC_QP_TIE_ABS 1e-12
 #define WBC_QP_DEP_TOL 1e-13
 #define WBC_QP_PIVOT_REL 1e-14
 
@@ -173,13 +179,11 @@ __device__ __forceinline__ QpResult warp_qp_solve_rt(const QpShared S, const int
     } else {
       S.vx[lane] = x;
       __syncwarp();
-      double best = 0.0;
-      int bidx = 0x7fffffff;
+      double vb = INFINITY, vc = INFINITY;
       int myside_b = -1, myside_c = -1;
       if (lane < n && bstat == 0) {
         const double slo = x - lb, sup = ub - x;
-        best = fmin(slo, sup);
-        bidx = lane;
+        vb = fmin(slo, sup);
         myside_b = (slo <= sup) ? -1 : +1;
       }
       if (lane < nC && cstat == 0) {
@@ -187,14 +191,16 @@ __device__ __forceinline__ QpResult warp_qp_solve_rt(const QpShared S, const int
         double ax = 0.0;
         for (int j = 0; j < n; ++j) ax += Cr[j] * S.vx[j];
         const double slo = ax - clb, sup = cub - ax;
-        const double v = fmin(slo, sup);
+        vc = fmin(slo, sup);
         myside_c = (slo <= sup) ? -1 : +1;
-        if (v < best || bidx == 0x7fffffff) { best = v; bidx = n + lane; }
       }
-      if (bidx == 0x7fffffff) best = 0.0;
-      warp_argmin(best, bidx);
+      double best = fmin(vb, vc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(WBC_FULL_MASK, best, o));
       if (!(best < -WBC_QP_FEAS_TOL)) break;
-      ip = bidx;
+      const double thr = best + (WBC_QP_TIE_ABS + WBC_QP_TIE_REL * fabs(best));   // lowest index inside the tie window
+      const unsigned wb = __ballot_sync(WBC_FULL_MASK, vb <= thr), wc = __ballot_sync(WBC_FULL_MASK, vc <= thr);
+      ip = wb ? __ffs(wb) - 1 : n + __ffs(wc) - 1;
       const int src = (ip < n) ? ip : ip - n;
       side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);
     }

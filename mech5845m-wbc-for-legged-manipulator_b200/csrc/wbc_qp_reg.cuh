@@ -558,8 +558,9 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
     if (!have) {
       // ------------------------------------------------------------ pick the entering constraint
       {
-        // most violated side over the boxes (index lane) and the rows (index n + lane), ties to the lowest index:
-        // a min-reduction of the value, then two votes (every box index is below every row index)
+        // most violated side over the boxes (index lane) and the rows (index n + lane), ties (within the window of
+        // wbc_qp.cuh) to the lowest index: a min-reduction of the value, then two votes (every box index is below every
+        // row index)
         double vb = INFINITY, vc = INFINITY;
         int myside_b = -1, myside_c = -1;
         if (act && bstat == 0) {
@@ -576,7 +577,8 @@ __device__ __forceinline__ QpResult warp_qp_solve_reg_impl(const QpRegShared S, 
         if (!__any_sync(WBC_FULL_MASK, best < -WBC_QP_FEAS_TOL)) break;   // primal feasible: optimal (the usual exit)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(WBC_FULL_MASK, best, o));
-        const unsigned wb = __ballot_sync(WBC_FULL_MASK, vb == best), wc = __ballot_sync(WBC_FULL_MASK, vc == best);
+        const double thr = best + (WBC_QP_TIE_ABS + WBC_QP_TIE_REL * fabs(best));     // tie window (wbc_qp.cuh)
+        const unsigned wb = __ballot_sync(WBC_FULL_MASK, vb <= thr), wc = __ballot_sync(WBC_FULL_MASK, vc <= thr);
         ip = wb ? __ffs(wb) - 1 : n + __ffs(wc) - 1;
         const int src = (ip < n) ? ip : ip - n;
         side = __shfl_sync(WBC_FULL_MASK, (ip < n) ? myside_b : myside_c, src);

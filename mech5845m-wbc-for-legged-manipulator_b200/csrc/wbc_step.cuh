@@ -17,6 +17,9 @@
 #define WBC_IN_TARGETS 34   // 18
 #define WBC_IN_MEM 52       // 72
 #define WBC_IN_REF 124      // 24
+#define WBC_IN_IMU 28       // 4: the IMU quaternion fed back after the tick (runWBC's base_config) -- in the tail of the q
+                            //    slot (the fused kernel is instantiated for nq <= 28 only), so that the block stays 148 wide:
+                            //    the general instantiation's 12 warps per SM fill the 227 KB of shared memory to the byte
 #define WBC_IN_TOTAL 148
 #define WBC_HOT_FRAMES 6
 #define WBC_STEP_FLAG_WEIGHTS_IDENTITY 0x10000   // internal (set by the host wrapper): every 6x6 task weight is I
@@ -78,7 +81,18 @@ struct StepParams {
   int red_ok;
   unsigned red_rows, red_feet_mask, red_blk;
   int grid_cap;                                   // > 0: at most this many CTAs (wbc_step_host runs two slices side by side)
+  // optional FP32 I/O (wbc_step_host with WBC_HOST_F32): which arrays hold float32 elements instead of float64
+  int f32_in;                                     // WBC_F32_Q | _TARGETS | _MEM | _REF | _IMU
+  int f32_out;                                    // WBC_F32_QDOT | _JOINTS
 };
+#define WBC_F32_Q 1
+#define WBC_F32_TARGETS 2
+#define WBC_F32_MEM 4
+#define WBC_F32_REF 8
+#define WBC_F32_IMU 16
+#define WBC_F32_DELTA 32       // float32 targets / IMU quaternion are increments over the previous targets / the resident quaternion
+#define WBC_F32_QDOT 1
+#define WBC_F32_JOINTS 2
 
 // Row layout of C implied by the constraint mask (findConstraints order, Robot_Wrapper4.py:764-836): computed once on
 // the host so that the kernel reads the offsets straight from the parameter bank.
@@ -164,22 +178,94 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const double* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// fetch the input block of state s: q, targets, task memory, references (1128 B for nq = 27), coalesced
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+
+// one input array of the state: n elements into the slot at `slot_a` (n doubles wide).  float64: element i lands in its
+// place; float32 (optional FP32 I/O): the n floats land in the upper half of the slot, widen_slot() spreads them out.
+__device__ __forceinline__ void prefetch_slot(uint32_t slot_a, const double* src, long long s, int n, bool f32, int lane) {
+  if (!f32) {
+    const double* g = src + s * n;
+    for (int i = lane; i < n; i += 32) cp_async8(slot_a + 8 * i, g + i);
+  } else {
+    const float* g = reinterpret_cast<const float*>(src) + s * n;
+    for (int i = lane; i < n; i += 32) cp_async4(slot_a + 4 * n + 4 * i, g + i);
+  }
+}
+
+// fetch the input block of state s: q, targets, task memory, references (+ the IMU quaternion): 1128 (+ 32) B for
+// nq = 27, coalesced
 template <int NV>
-__device__ __forceinline__ void prefetch_inputs(const WbcStepIO& io, long long s, uint32_t in_a, int lane) {
+__device__ __forceinline__ void prefetch_inputs(const StepParams& P, long long s, uint32_t in_a, int lane) {
   constexpr int nq = NV + 1;
-  const double* qg = io.q + s * nq;
-  if (lane < nq) cp_async8(in_a + 8 * (WBC_IN_Q + lane), qg + lane);
-  if (nq > 32 && lane == 0) cp_async8(in_a + 8 * (WBC_IN_Q + 32), qg + 32);
-  const double* tg = io.targets + s * WBC_TARGETS_STRIDE;
-  if (lane < WBC_TARGETS_STRIDE) cp_async8(in_a + 8 * (WBC_IN_TARGETS + lane), tg + lane);
-  const double* mg = io.mem_in + s * WBC_MEM_STRIDE;
-  cp_async8(in_a + 8 * (WBC_IN_MEM + lane), mg + lane);
-  cp_async8(in_a + 8 * (WBC_IN_MEM + 32 + lane), mg + 32 + lane);
-  if (lane < WBC_MEM_STRIDE - 64) cp_async8(in_a + 8 * (WBC_IN_MEM + 64 + lane), mg + 64 + lane);
-  const double* rg = io.ref + s * WBC_REF_STRIDE;
-  if (lane < WBC_REF_STRIDE) cp_async8(in_a + 8 * (WBC_IN_REF + lane), rg + lane);
+  const WbcStepIO& io = P.io;
+  if (P.f32_in == 0) {                           // (uniform) the float64 layout: straight-line, one instruction per 32 doubles
+    const double* qg = io.q + s * nq;
+    if (lane < nq) cp_async8(in_a + 8 * (WBC_IN_Q + lane), qg + lane);
+    if (nq > 32 && lane == 0) cp_async8(in_a + 8 * (WBC_IN_Q + 32), qg + 32);
+    const double* tg = io.targets + s * WBC_TARGETS_STRIDE;
+    if (lane < WBC_TARGETS_STRIDE) cp_async8(in_a + 8 * (WBC_IN_TARGETS + lane), tg + lane);
+    const double* mg = io.mem_in + s * WBC_MEM_STRIDE;
+    cp_async8(in_a + 8 * (WBC_IN_MEM + lane), mg + lane);
+    cp_async8(in_a + 8 * (WBC_IN_MEM + 32 + lane), mg + 32 + lane);
+    if (lane < WBC_MEM_STRIDE - 64) cp_async8(in_a + 8 * (WBC_IN_MEM + 64 + lane), mg + 64 + lane);
+    const double* rg = io.ref + s * WBC_REF_STRIDE;
+    if (lane < WBC_REF_STRIDE) cp_async8(in_a + 8 * (WBC_IN_REF + lane), rg + lane);
+    if (io.imu_quat && lane < 4) cp_async8(in_a + 8 * (WBC_IN_IMU + lane), io.imu_quat + s * 4 + lane);
+  } else {
+    prefetch_slot(in_a + 8 * WBC_IN_Q, io.q, s, nq, P.f32_in & WBC_F32_Q, lane);
+    prefetch_slot(in_a + 8 * WBC_IN_TARGETS, io.targets, s, WBC_TARGETS_STRIDE, P.f32_in & WBC_F32_TARGETS, lane);
+    prefetch_slot(in_a + 8 * WBC_IN_MEM, io.mem_in, s, WBC_MEM_STRIDE, P.f32_in & WBC_F32_MEM, lane);
+    prefetch_slot(in_a + 8 * WBC_IN_REF, io.ref, s, WBC_REF_STRIDE, P.f32_in & WBC_F32_REF, lane);
+    if (io.imu_quat) prefetch_slot(in_a + 8 * WBC_IN_IMU, io.imu_quat, s, 4, P.f32_in & WBC_F32_IMU, lane);
+  }
   cp_async_commit();
+}
+
+// FP32 I/O: the float32 elements that prefetch_slot() parked in the upper halves of their slots become float64 in
+// place (all reads of the warp precede all writes: the two ranges overlap)
+template <int NV>
+__device__ __forceinline__ void widen_inputs(const StepParams& P, uint32_t in_a, int lane) {
+  constexpr int nq = NV + 1;
+  const int m = P.f32_in;
+  float vq = 0.f, vq2 = 0.f, vt = 0.f, vm0 = 0.f, vm1 = 0.f, vm2 = 0.f, vr = 0.f, vi = 0.f;
+  if ((m & WBC_F32_Q) && lane < nq) vq = lds_f32(in_a + 8 * WBC_IN_Q + 4 * nq + 4 * lane);
+  if ((m & WBC_F32_Q) && nq > 32 && lane == 0) vq2 = lds_f32(in_a + 8 * WBC_IN_Q + 4 * nq + 4 * 32);
+  if ((m & WBC_F32_TARGETS) && lane < WBC_TARGETS_STRIDE) vt = lds_f32(in_a + 8 * WBC_IN_TARGETS + 4 * WBC_TARGETS_STRIDE + 4 * lane);
+  if (m & WBC_F32_MEM) {
+    const uint32_t a = in_a + 8 * WBC_IN_MEM + 4 * WBC_MEM_STRIDE + 4 * lane;
+    vm0 = lds_f32(a); vm1 = lds_f32(a + 128);
+    if (lane < WBC_MEM_STRIDE - 64) vm2 = lds_f32(a + 256);
+  }
+  if ((m & WBC_F32_REF) && lane < WBC_REF_STRIDE) vr = lds_f32(in_a + 8 * WBC_IN_REF + 4 * WBC_REF_STRIDE + 4 * lane);
+  if ((m & WBC_F32_IMU) && P.io.imu_quat && lane < 4) vi = lds_f32(in_a + 8 * WBC_IN_IMU + 16 + 4 * lane);
+  __syncwarp();
+  if ((m & WBC_F32_Q) && lane < nq) sts_f64(in_a + 8 * (WBC_IN_Q + lane), (double)vq);
+  if ((m & WBC_F32_Q) && nq > 32 && lane == 0) sts_f64(in_a + 8 * (WBC_IN_Q + 32), (double)vq2);
+  if ((m & WBC_F32_TARGETS) && lane < WBC_TARGETS_STRIDE) {
+    double t = (double)vt;
+    if (m & WBC_F32_DELTA)       // increment over the previous tick's target: prev_EE_pos[5][3] | prev_trunk_ref[3] of the task memory
+      t += lds_f64(in_a + 8 * (WBC_IN_MEM + (lane < 15 ? MEM_PREV_EE_POS + lane : MEM_PREV_TRUNK_REF + lane - 15)));
+    sts_f64(in_a + 8 * (WBC_IN_TARGETS + lane), t);
+  }
+  if (m & WBC_F32_MEM) {
+    sts_f64(in_a + 8 * (WBC_IN_MEM + lane), (double)vm0);
+    sts_f64(in_a + 8 * (WBC_IN_MEM + 32 + lane), (double)vm1);
+    if (lane < WBC_MEM_STRIDE - 64) sts_f64(in_a + 8 * (WBC_IN_MEM + 64 + lane), (double)vm2);
+  }
+  if ((m & WBC_F32_REF) && lane < WBC_REF_STRIDE) sts_f64(in_a + 8 * (WBC_IN_REF + lane), (double)vr);
+  if ((m & WBC_F32_IMU) && P.io.imu_quat && lane < 4) {
+    double t = (double)vi;
+    if (m & WBC_F32_DELTA) t += lds_f64(in_a + 8 * (WBC_IN_Q + 3 + lane));     // increment over the resident base quaternion
+    sts_f64(in_a + 8 * (WBC_IN_IMU + lane), t);
+  }
+  __syncwarp();
 }
 
 #define WBC_MOFF(f) ((uint32_t)offsetof(DevModel, f))
@@ -518,6 +604,7 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0, bool RED = false>
 __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws) {
   constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
+  static_assert(NV + 1 <= WBC_IN_IMU, "the IMU quaternion sits behind q inside the q slot");
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
   constexpr int LD = NV | 1;
   constexpr int nq = NV + 1;
@@ -551,7 +638,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
   {
     long long s0 = (long long)blockIdx.x * wpc + warp;
     if (s0 >= P.N) s0 = P.N - 1;
-    prefetch_inputs<NV>(P.io, s0, in0_a, lane);
+    prefetch_inputs<NV>(P, s0, in0_a, lane);
   }
   for (long long base = (long long)blockIdx.x * wpc; base < P.N; base += stride) {
     long long sidx = base + warp;
@@ -562,7 +649,17 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     const uint32_t q_a = in_a + 8 * WBC_IN_Q, tg_a = in_a + 8 * WBC_IN_TARGETS;
     const uint32_t mem_a = in_a + 8 * WBC_IN_MEM, ref_a = in_a + 8 * WBC_IN_REF;
     cp_async_wait_all();
+    if (P.f32_in) widen_inputs<NV>(P, in_a, lane);       // (uniform) optional FP32 I/O
     phase_sync<PS && (WBC_SYNC_TOP != 0)>();
+    // the next state's inputs travel while this tick computes: the other buffer is free (its last reader was the tail
+    // of the previous tick), and a whole tick -- ~20 us per warp -- hides the latency even of a PCIe read (zero-copy
+    // host buffers).  Issued here, not in front of the QP, so that its address arithmetic does not sit in the kernel's
+    // region of highest register pressure.
+    if (base + stride < P.N) {
+      long long ns = base + stride + warp;
+      if (ns >= P.N) ns = P.N - 1;
+      prefetch_inputs<NV>(P, ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
+    }
 
     // ---------------------------------------------------------------- kinematics
     double Sc[6];                        // column `lane` of data.J (WORLD): [lin; ang]
@@ -951,21 +1048,11 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       if (P.io.mem_out)
         for (int i = lane; i < WBC_MEM_STRIDE; i += 32) P.io.mem_out[sidx * WBC_MEM_STRIDE + i] = lds_f64(mem_a + 8 * i);
       __syncwarp();
-      if (base + stride < P.N) {
-        long long ns = base + stride + warp;
-        if (ns >= P.N) ns = P.N - 1;
-        prefetch_inputs<NV>(P.io, ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
-      }
       buf ^= 1;
       continue;
     }
 
-    // ---------------------------------------------------------------- next state's inputs, then the QP
-    if (base + stride < P.N) {
-      long long ns = base + stride + warp;
-      if (ns >= P.N) ns = P.N - 1;
-      prefetch_inputs<NV>(P.io, ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
-    }
+    // ---------------------------------------------------------------- the QP
     double x;
     QpResult res;
     {
@@ -985,7 +1072,10 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     }
 
     phase_sync<PS && (WBC_SYNC_POSTQP != 0)>();
-    if (valid && lane < NV) P.io.qdot[sidx * NV + lane] = x;
+    if (valid && lane < NV) {
+      if (P.f32_out & WBC_F32_QDOT) reinterpret_cast<float*>(P.io.qdot)[sidx * NV + lane] = (float)x;
+      else P.io.qdot[sidx * NV + lane] = x;
+    }
     if (valid && lane == 0) {
       P.io.status[sidx] = res.status;
       P.io.iters[sidx] = res.iters;
@@ -1021,7 +1111,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       if (!(P.flags & WBC_STEP_FLAG_PLAIN_INTEGRATE)) {
         // updateState(joint_config, imu, running=True): q = [old xyz, imu quat, joints], FK, trunkWorldPos (:387-428)
         if (lane < 3) sts_f64(qn_a + 8 * lane, lds_f64(q_a + 8 * lane));
-        if (P.io.imu_quat && lane < 4) sts_f64(qn_a + 8 * (3 + lane), P.io.imu_quat[sidx * 4 + lane]);
+        if (P.io.imu_quat && lane < 4) sts_f64(qn_a + 8 * (3 + lane), lds_f64(in_a + 8 * (WBC_IN_IMU + lane)));
         __syncwarp();
         warp_fk_a(M_a, qn_a, omi_a, lane);
         double bp[3] = {0, 0, 0};
@@ -1062,6 +1152,11 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       }
       if (valid)
         for (int i = lane; i < nq; i += 32) P.io.q_next[sidx * nq + i] = lds_f64(qn_a + 8 * i);
+      if (valid && P.io.joint_targets && lane < nq - 7) {      // what runWBC returns: q_next[7:] (:1405-1412)
+        const double jt = lds_f64(qn_a + 8 * (7 + lane));
+        if (P.f32_out & WBC_F32_JOINTS) reinterpret_cast<float*>(P.io.joint_targets)[sidx * (nq - 7) + lane] = (float)jt;
+        else P.io.joint_targets[sidx * (nq - 7) + lane] = jt;
+      }
       __syncwarp();
     }
     buf ^= 1;

@@ -90,6 +90,33 @@ class LinearTrajectory:
         return self.m[i] + u * (self.m[i + 1] - self.m[i])
 
 
+class HostDeltaEncoder:
+    """Host-side twin of the FP32 increment inputs of ``RobotModel.step_host(..., delta_inputs=True)``: keeps float64
+    mirrors of what the device holds as "previous targets" (task memory ``prev_EE_pos`` / ``prev_trunk_ref``) and as base
+    quaternion, hands out float32 increments and advances the mirrors with exactly the float64 additions the kernel
+    performs, so host and device never drift apart."""
+
+    def __init__(self, robot):
+        m = robot._mem
+        self.prev_targets = torch.cat((m[:, 0:15], m[:, 60:63]), dim=1).cpu().clone()
+        self.quat = robot.current_joint_config[:, 3:7].cpu().clone()
+
+    def encode(self, targets, imu=None, out_targets=None, out_imu=None):
+        """targets [N, 18] (and imu [N, 4]) float64 CPU tensors -> float32 increments (written into the given pinned
+        buffers when supplied)."""
+        dt = (targets - self.prev_targets).to(torch.float32)
+        self.prev_targets += dt.double()
+        if out_targets is not None:
+            out_targets.copy_(dt); dt = out_targets
+        if imu is None:
+            return dt, None
+        di = (imu - self.quat).to(torch.float32)
+        self.quat += di.double()
+        if out_imu is not None:
+            out_imu.copy_(di); di = out_imu
+        return dt, di
+
+
 class RobotModel:
     def __init__(self, urdf_path, mesh_dir_path=None, EE_frame_names=EE_FRAME_NAMES, EE_joint_names=EE_JOINT_NAMES,
                  G_base="waist", imu="imu_joint", FR_hip_joint="FR_hip_joint",
@@ -427,8 +454,7 @@ class RobotModel:
             config = self._as_batch(joint_config, nq).clone()
         self._refresh(config)
         if running is True:
-            base_pos = self.trunkWorldPos()                                              # :414
-            config = torch.cat((base_pos, self.current_joint_config[:, 3:]), dim=1).contiguous()
+            config = self._base_estimate(config, want_config=True)                       # trunkWorldPos (:414)
             self._refresh(config)                                                        # :418-428
 
     def getFrameJacobian(self, frame_id, reference_frame):
@@ -593,14 +619,19 @@ class RobotModel:
         return self._assemble(self._config(), list(want), targets=T, mem_out=self._mem if update_memory else None)
 
     # ---------------------------------------------------------------------------------- :1297-1327
+    def _base_estimate(self, config, want_config=False):
+        """``wbc_base_estimate``: FK at ``config`` and the base position estimate from the four foot targets."""
+        out = torch.empty_like(config) if want_config else torch.empty(self.N, 3, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.wbc_base_estimate(self._model, _ptr(config), None, _ptr(self._targets), self.N,
+                                                   _ptr(out) if want_config else None,
+                                                   None if want_config else _ptr(out), _stream_ptr()))
+        return out
+
     def trunkWorldPos(self):
-        WRB = self._oMf[:, cabi.FRAME_TRUNK, :9].reshape(self.N, 3, 3)
-        trunk_pos = self._oMf[:, cabi.FRAME_TRUNK, 9:12]
-        BPA = ((self._oMf[:, 0, 9:12] - trunk_pos) + (self._oMf[:, 1, 9:12] - trunk_pos)
-               + (self._oMf[:, 2, 9:12] - trunk_pos) + (self._oMf[:, 3, 9:12] - trunk_pos)) / 4
-        T = self._targets
-        WPA = (T[:, 0:3] + T[:, 3:6] + T[:, 6:9] + T[:, 9:12]) / 4
-        return WPA - torch.einsum("nij,nj->ni", WRB, BPA)
+        """[N, 3]: mean(foot targets) - R_trunk mean(foot - trunk) at the current configuration; the foot targets are the
+        ones of the last ``runWBC`` / ``qpb`` / ``step`` call (``FR_target_cartesian_pos`` ..., :1332-1335)."""
+        return self._base_estimate(self.current_joint_config.contiguous())
 
     # ---------------------------------------------------------------------------------- the fused tick :1330-1412
     def step(self, target_cartesian_pos_EE, target_cartesian_pos_trunk, imu_quat=None, advance=True,
@@ -627,32 +658,50 @@ class RobotModel:
             self.current_joint_config = q_next
         return self.qdot
 
-    def step_host(self, host_in, host_out, chunks=0, resident_state=False):
-        """The fused tick with HOST buffers (what a caller holding NumPy arrays pays end to end).
+    def step_host(self, host_in, host_out, chunks=0, resident_state=False, closed_loop=False, delta_inputs=False):
+        """One tick with HOST buffers (what a caller holding NumPy arrays pays end to end): one C-ABI call,
+        ``wbc_step_host``.
 
-        ``host_in``: dict of pinned float64 CPU tensors q [N, nq], targets [N, 18], mem [N, 72], ref [N, 24];
-        ``host_out``: dict of pinned CPU tensors qdot [N, nv], status [N] (int32), iters [N] (int32).
-        One C-ABI call (``wbc_step_host``).  ``chunks=0`` (default): with page-locked tensors the kernel reads the
+        ``closed_loop=True`` -- the tick ``runWBC`` actually is (Robot_Wrapper4.py:1330-1412): ``host_in`` carries this
+        tick's arguments, ``targets`` [N, 18] (5 EE targets + trunk target) and optionally ``imu`` [N, 4] (``base_config``);
+        the configuration, the task memory and the per-robot references are the controller's state and stay on the
+        device, advanced in place exactly as runWBC mutates its object (``prev_EE_pos`` ... :995-996, :1151-1152,
+        ``current_joint_config`` :1397-1402).  ``host_out`` receives ``joint_targets`` [N, nq - 7] (the five slices runWBC
+        returns, :1405-1412), ``status`` / ``iters`` [N] (int32) and, if present, ``qdot`` [N, nv].  K calls equal
+        ``rollout`` over the same K ticks.
+
+        ``closed_loop=False`` -- the open-loop tick: ``host_in`` = q [N, nq], targets [N, 18] (+ mem [N, 72], ref [N, 24]
+        unless ``resident_state``), ``host_out`` = qdot, status, iters; nothing on the device is advanced.
+
+        Float arrays are float64, or ALL float32 (the optional FP32 I/O mode: half the PCIe bytes, float64 arithmetic
+        inside).  ``delta_inputs`` (float32, closed loop): ``targets`` / ``imu`` hold INCREMENTS over the previous tick's
+        targets / the resident base quaternion (``HostDeltaEncoder`` produces them): a float32 increment is exact to
+        ~1e-10, so the mode agrees with the float64 call to < 1e-4 in qdot, where absolute float32 positions (error
+        ~3e-8, times 1 / dt = 500 in the target laws) only guarantee it for the joint position targets.  ``chunks=0``: with page-locked tensors the kernel reads the
         inputs from and writes the outputs to host memory directly (zero-copy, one launch); with pageable tensors, or
-        ``chunks >= 1``, the batch is cut into contiguous slices that go host -> device, through the fused kernel and
-        back on three streams owned by the model, so the PCIe copies of one slice overlap the kernel of another; the
-        current stream waits for all of them.  Returns (h2d_bytes, d2h_bytes): the bytes that cross PCIe either way.
-
-        ``resident_state``: only the per-tick inputs (q, targets) travel; the task memory and the per-robot references
-        stay where the reference keeps them -- in the controller object (``prev_EE_pos`` ... ``initial_trunk_pos``,
-        Robot_Wrapper4.py:133-140, 363-383), i.e. on the device.
+        ``chunks >= 1``, the batch is cut into slices that go host -> device, through the fused kernel and back on three
+        streams owned by the model; the current stream waits for all of them.  Returns (h2d_bytes, d2h_bytes).
         """
-        N = self.N
-        moved = ("q", "targets") if resident_state else ("q", "targets", "mem", "ref")
+        N, nq, nv = self.N, self.n_configuration_dimensions, self.n_velocity_dimensions
+        if closed_loop:
+            moved = ("targets",) + (("imu",) if host_in.get("imu") is not None else ())
+            outs = tuple(k for k in ("joint_targets", "qdot") if host_out.get(k) is not None)
+        else:
+            moved = ("q", "targets") if resident_state else ("q", "targets", "mem", "ref")
+            outs = ("qdot",)
+        fdt = host_in["targets"].dtype
+        if fdt not in (torch.float64, torch.float32):
+            raise ValueError("host arrays must be float64 or float32")
         for k in moved:
             t = host_in[k]
-            if t.device.type != "cpu" or t.dtype != torch.float64 or not t.is_contiguous():
-                raise ValueError(f"host_in[{k!r}] must be a contiguous float64 CPU tensor")
-        for k, dt_ in (("qdot", torch.float64), ("status", torch.int32), ("iters", torch.int32)):
-            t = host_out[k]
-            if t.device.type != "cpu" or t.dtype != dt_ or not t.is_contiguous():
-                raise ValueError(f"host_out[{k!r}] must be a contiguous {dt_} CPU tensor")
+            if t.device.type != "cpu" or t.dtype != fdt or not t.is_contiguous() or t.shape[0] != N:
+                raise ValueError(f"host_in[{k!r}] must be a contiguous {fdt} CPU tensor with {N} rows")
+        for k in outs + ("status", "iters"):
+            t, dt_ = host_out[k], (fdt if k in outs else torch.int32)
+            if t.device.type != "cpu" or t.dtype != dt_ or not t.is_contiguous() or t.shape[0] != N:
+                raise ValueError(f"host_out[{k!r}] must be a contiguous {dt_} CPU tensor with {N} rows")
         io = cabi.WbcStepIO()
+        self.current_joint_config = self.current_joint_config.contiguous()
         io.q = self.current_joint_config.data_ptr()
         io.targets = self._targets.data_ptr()
         io.mem_in = self._mem.data_ptr()
@@ -662,22 +711,45 @@ class RobotModel:
         io.status = self.last_status.data_ptr()
         io.iters = self.last_iters.data_ptr()
         host = cabi.WbcHostIO()
-        host.q = host_in["q"].data_ptr()
+        host.dtype = cabi.HOST_F32 if fdt == torch.float32 else cabi.HOST_F64
+        host.flags = cabi.HOST_FLAG_DELTA_INPUTS if delta_inputs else 0
         host.targets = host_in["targets"].data_ptr()
-        if not resident_state:
-            host.mem_in = host_in["mem"].data_ptr()
-            host.ref = host_in["ref"].data_ptr()
-        host.qdot = host_out["qdot"].data_ptr()
+        if closed_loop:
+            if getattr(self, "_stage_imu", None) is None:                               # staging space of the sliced path
+                self._stage_imu = torch.empty(N, 4, dtype=torch.float64, device=self.device)
+                self._stage_joints = torch.empty(N, nq - 7, dtype=torch.float64, device=self.device)
+            io.q_next = io.q
+            io.mem_out = io.mem_in
+            io.joint_targets = self._stage_joints.data_ptr()
+            if "imu" in moved:
+                io.imu_quat = self._stage_imu.data_ptr()
+                host.imu_quat = host_in["imu"].data_ptr()
+            if "joint_targets" in outs:
+                host.joint_targets = host_out["joint_targets"].data_ptr()
+            if "qdot" in outs:
+                host.qdot = host_out["qdot"].data_ptr()
+        else:
+            host.q = host_in["q"].data_ptr()
+            if not resident_state:
+                host.mem_in = host_in["mem"].data_ptr()
+                host.ref = host_in["ref"].data_ptr()
+            host.qdot = host_out["qdot"].data_ptr()
         host.status = host_out["status"].data_ptr()
         host.iters = host_out["iters"].data_ptr()
         with torch.cuda.device(self.device):
             cabi.check(self._lib.wbc_step_host(self._model, C.byref(self._config()), C.byref(io), C.byref(host), N,
                                                int(chunks), _stream_ptr()))
-        h2d = sum(host_in[k].numel() * 8 for k in moved)
-        d2h = host_out["qdot"].numel() * 8 + host_out["status"].numel() * 4 + host_out["iters"].numel() * 4
+        if closed_loop:
+            self.firstQP = False
+        esz = 4 if fdt == torch.float32 else 8
+        h2d = sum(host_in[k].numel() * esz for k in moved)
+        d2h = sum(host_out[k].numel() * esz for k in outs) + host_out["status"].numel() * 4 + host_out["iters"].numel() * 4
         return h2d, d2h
 
     def runWBC(self, base_config, target_cartesian_pos_EE=None, target_cartesian_pos_trunk=None):
+        """Robot_Wrapper4.py:1330-1412, batched.  Like the reference, the QP's report is not acted upon: a state whose QP
+        hit the iteration cap or was infeasible (``last_status`` != 0) is integrated with whatever the solver held, as
+        qpOASES' primal vector is used unchecked (QP_Wrapper.py:45-51).  ``check_status()`` raises on such states."""
         self.step(target_cartesian_pos_EE, target_cartesian_pos_trunk, imu_quat=base_config, advance=True)
         self.firstQP = False
         self._refresh(self.current_joint_config)           # keep the accessor caches (oMf, J) on the new state
@@ -719,6 +791,13 @@ class RobotModel:
             qs.append(self.current_joint_config.clone()); vs.append(self.qdot.clone()); st.append(self.last_status.clone())
         self.firstQP = False
         return torch.stack(qs), torch.stack(vs), torch.stack(st)
+
+    def check_status(self):
+        """Raise if any state's last QP did not end with WBC_QP_SOLVED (the reference silently ignores qpOASES' return
+        value; callers that integrate ``runWBC`` / ``rollout`` results blindly may want this).  Synchronises."""
+        bad = int((self.last_status != 0).sum().item())
+        if bad:
+            raise cabi.WbcError(f"{bad} of {self.N} states: QP not solved (status bits: 1 iteration cap, 2 infeasible, 4 not PD)")
 
     def launch_info(self):
         g, b, s, r = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()

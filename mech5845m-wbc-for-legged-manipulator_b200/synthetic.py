@@ -76,6 +76,50 @@ def load_batch(robot, q, noise):
     return targets.contiguous()
 
 
+def config3_rows(table, mu=0.6, duty=0.005, payload=0.2, gravity=9.81):
+    """Constraint rows of BASELINE config 3 ("A1 + WX200 with friction-cone + torque-limit constraints") for the generic
+    extension-row channel (``RobotModel.extra_rows`` -> ``WbcConfig.extra_*``): tuples (frame slot, reference frame,
+    coeff[6], lo, hi), row = coeff . J_frame(rf), lo <= row . qdot <= hi.
+
+    NOT in the reference: its QP is purely kinematic (no contact forces, no torques), so both
+    families are velocity-space stand-ins, used with the four foot equality constraints switched OFF:
+
+      * friction pyramid, 4 faces per foot (16 rows): the LOCAL_WORLD_ALIGNED foot velocity v stays inside
+        +-v_x <= mu v_z, +-v_y <= mu v_z (a contact may only lift off inside the cone; v = 0 is the apex);
+      * torque-limit proxy by virtual work (7 rows): the joints of a limb deliver the power f . v against the load f
+        they carry, and that power is capped by a fraction `duty` of the limb's rated power sum_k effort_k velocity_k
+        (URDF <limit effort= velocity=>, pin.Model.effortLimit / velocityLimit).  Stance leg i carries a quarter of
+        the weight: |(M g / 4) v_z(foot i)| <= P_leg (4 rows); the arm carries its distal links plus a payload:
+        |m g v_z(gripper)| <= P_arm, and its wrist torque: |tau_wrist w_x|, |tau_wrist w_y| <= P_arm (3 rows).
+    """
+    big, LWA = 1e30, 2
+    rows = []
+    for foot in range(4):
+        for cx, cy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            rows.append((foot, LWA, [cx, cy, -mu, 0, 0, 0], -big, 0.0))
+    eff = np.asarray(table.effort, dtype=float)
+    vel = np.asarray(table.velocity, dtype=float)
+    total_mass = float(np.sum(table.mass))
+    fz = total_mass * gravity / 4.0
+    for foot in range(4):
+        j = table.frame_parent[table.getFrameId(["FR_foot_fixed", "FL_foot_fixed", "RR_foot_fixed", "RL_foot_fixed"][foot],
+                                                "FIXED_JOINT")]
+        iv = table.idx_v[j]                                   # calf joint: the leg's columns are [iv - 2, iv]
+        p_leg = duty * float(np.sum(eff[iv - 2:iv + 1] * vel[iv - 2:iv + 1]))
+        rows.append((foot, LWA, [0, 0, fz, 0, 0, 0], -p_leg, p_leg))
+    jw = table.getJointId("waist")
+    jg = table.getJointId("gripper")
+    if jw < table.njoints and jg < table.njoints:
+        arm = range(table.idx_v[jw], table.idx_v[jg])         # waist .. wrist joints
+        p_arm = duty * float(sum(eff[k] * vel[k] for k in arm))
+        m_arm = float(sum(table.mass[j] for j in range(jw + 2, table.njoints))) + payload
+        tau_w = float(eff[table.idx_v[jg] - 1])
+        rows.append((4, LWA, [0, 0, m_arm * gravity, 0, 0, 0], -p_arm, p_arm))
+        rows.append((4, LWA, [0, 0, 0, tau_w, 0, 0], -p_arm, p_arm))
+        rows.append((4, LWA, [0, 0, 0, 0, tau_w, 0], -p_arm, p_arm))
+    return rows
+
+
 def rank_slice(N, rank, world):
     """Contiguous shard [lo, hi) of N states for `rank` of `world`."""
     per = (N + world - 1) // world

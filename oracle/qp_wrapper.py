@@ -20,8 +20,11 @@ Every solution carries a KKT certificate (``kkt_residuals``).
 Pivoting rules shared with the CUDA kernel (csrc/wbc_qp.cuh):
   * constraints are numbered c = 0..nv-1 (box on x_c) then nv..nv+nC-1 (rows of C);
   * equalities (lo == up) enter first, in index order;
-  * the entering constraint is the most violated side, s = min(a.x - lo, up - a.x) < -FEAS_TOL,
-    ties broken by the lowest index;
+  * the entering constraint is the most violated side, s = min(a.x - lo, up - a.x) < -FEAS_TOL;
+    candidates within TIE_ABS + TIE_REL |s_min| of the minimum count as tied and the lowest index wins.  (Mirrored
+    rows -- e.g. the +-x faces of a friction pyramid once their partners are active -- tie EXACTLY in exact
+    arithmetic; without the window the winner is decided by rounding noise, which differs between an incrementally
+    updated C x and a fresh product);
   * the leaving constraint is the active inequality with the smallest ratio u_k / r_k, r_k > 0,
     ties broken by the earliest position in the working set;
   * a candidate whose normal is dependent on the working set (z.n <= DEP_TOL * d.d) takes a
@@ -30,6 +33,8 @@ Pivoting rules shared with the CUDA kernel (csrc/wbc_qp.cuh):
 import numpy as np
 
 FEAS_TOL = 1e-10
+TIE_REL = 1e-9
+TIE_ABS = 1e-12
 DEP_TOL = 1e-13
 PIVOT_REL = 1e-14
 
@@ -132,9 +137,10 @@ def solve_qp(H, g, lb, ub, C=None, Clb=None, Cub=None, max_iter=200):
             in_ws[c] = True
         viol = np.minimum(s_lo, s_up)
         viol[in_ws] = 0.0
-        ip = int(np.argmin(viol))                                     # first minimum wins
-        if not (viol[ip] < -FEAS_TOL):
+        vmin = float(np.min(viol))
+        if not (vmin < -FEAS_TOL):
             break
+        ip = int(np.argmax(viol <= vmin + (TIE_ABS + TIE_REL * abs(vmin))))   # lowest index inside the tie window
         side = -1 if s_lo[ip] <= s_up[ip] else +1
         nrm = normal(ip, side)
         bnd = lo[ip] if side < 0 else -up[ip]                         # n.x >= bnd
@@ -236,6 +242,7 @@ class QP:
         self.no_solutions = n_of_velocity_dimensions
         self.qp = None
         self.result = None
+        self.max_iter = 200        # working-set iteration cap (the reference hands qpOASES nWSR = 100000, QP_Wrapper.py:20)
 
     def _C_rows(self):
         # The reference passes C.T (Robot_Wrapper4.py:836) and sizes SQProblem with C.shape[1]
@@ -251,9 +258,10 @@ class QP:
 
     def solveQP(self):
         if self.C is None or self.Clb is None or self.Cub is None:
-            self.result = solve_qp(self.H, self.g, self.lb, self.ub)
+            self.result = solve_qp(self.H, self.g, self.lb, self.ub, max_iter=self.max_iter)
         else:
-            self.result = solve_qp(self.H, self.g, self.lb, self.ub, self._C_rows(), self.Clb, self.Cub)
+            self.result = solve_qp(self.H, self.g, self.lb, self.ub, self._C_rows(), self.Clb, self.Cub,
+                                   max_iter=self.max_iter)
         self.qp = True
         self.xOpt = self.result["x"]
         return self.xOpt
@@ -264,6 +272,6 @@ class QP:
         self.lb, self.ub, self.Clb, self.Cub, self.C = lb, ub, Clb, Cub, C
         self.H = np.dot(A.T, A)
         self.g = np.dot(-A.T, b)
-        self.result = solve_qp(self.H, self.g, lb, ub, self._C_rows(), Clb, Cub)
+        self.result = solve_qp(self.H, self.g, lb, ub, self._C_rows(), Clb, Cub, max_iter=self.max_iter)
         self.xOpt = self.result["x"]
         return self.xOpt

@@ -353,7 +353,12 @@ class RobotModel:
                 upper_pos_lim[i] = 0
         lower_pos_lim = np.delete(lower_pos_lim, 6)
         upper_pos_lim = np.delete(upper_pos_lim, 6)
+        # :603-619 index joint i's limits with current_joint_config[i], but the limit arrays had entry 6 deleted and the
+        # configuration did not (off-by-one from the first revolute joint on): reproduced by default;
+        # compat_damper_off_by_one = False compares joint i with its own coordinate
         cfg = self.current_joint_config
+        if not getattr(self, "compat_damper_off_by_one", True):
+            cfg = np.delete(cfg, 6)
         for i in range(len(lower_pos_lim)):                                            # :603-619 (off-by-one, D.2)
             if cfg[i] <= (lower_pos_lim[i] + qi):
                 lb[i] = -damping_coef * (cfg[i] - lower_pos_lim[i] - qs) / (qi - qs)
@@ -633,6 +638,7 @@ class RobotModel:
         lb, ub = self.velDamperJointConstraints()                                      # :1361
         if self.firstQP is True:                                                       # :1389-1394
             self.qp = QP(A, b, lb, ub, C, Clb, Cub, n_of_velocity_dimensions=self.n_velocity_dimensions)
+            self.qp.max_iter = getattr(self, "max_qp_iterations", 200)
             q_vel = self.qp.solveQP()
             self.firstQP = False
         else:

@@ -30,6 +30,8 @@
 #define MMAX (36 + WBC_MAX_NV)
 #define NCMAX WBC_MAX_NC
 #define FEAS_TOL 1e-10
+#define TIE_REL 1e-9           /* entering constraint: candidates within TIE_ABS + TIE_REL |min| of the most violated one */
+#define TIE_ABS 1e-12          /* are tied, the lowest index wins (oracle/qp_wrapper.py) */
 #define DEP_TOL 1e-13
 #define PIVOT_REL 1e-14
 #define MEM_OFF_PREV_EE_POS(i) (3 * (i))          /* layout of the task-memory block, include/wbc_b200.h */
@@ -313,17 +315,24 @@ static void qp_solve(int n, int nC, double H[NVMAX][NVMAX], const double* g, con
       if (lo == up) { ip = c; is_eq = 1; break; }
     }
     if (ip < 0) {
-      double best = 0.0;
+      double best = 0.0, viol[NVMAX + NCMAX];
+      int vside[NVMAX + NCMAX];
       for (int c = 0; c < m; ++c) {
+        viol[c] = 0.0; vside[c] = -1;
         if ((c < n ? bstat[c] : cstat[c - n]) != 0) continue;
         double ax, lo, up;
         if (c < n) { ax = x[c]; lo = lb[c]; up = ub[c]; }
         else { ax = 0; for (int j = 0; j < n; ++j) ax += C[c - n][j] * x[j]; lo = clb[c - n]; up = cub[c - n]; }
         const double slo = ax - lo, sup = up - ax;
-        const double v = slo < sup ? slo : sup;
-        if (v < best) { best = v; ip = c; side = (slo <= sup) ? -1 : +1; }
+        viol[c] = slo < sup ? slo : sup;
+        vside[c] = (slo <= sup) ? -1 : +1;
+        if (viol[c] < best) best = viol[c];
       }
-      if (ip < 0 || !(best < -FEAS_TOL)) break;
+      if (!(best < -FEAS_TOL)) break;
+      const double thr = best + (TIE_ABS + TIE_REL * fabs(best));       /* lowest index inside the tie window */
+      for (int c = 0; c < m; ++c)
+        if ((c < n ? bstat[c] : cstat[c - n]) == 0 && viol[c] <= thr) { ip = c; side = vside[c]; break; }
+      if (ip < 0) break;
     }
     const double sgn = (side > 0) ? -1.0 : 1.0;
     double nrm_v[NVMAX];

@@ -46,6 +46,9 @@ def copy_settings(src, dst):
               "const_active_RL_foot", "const_active_GRIP", "trunk_weight", "EE_weight", "cart_task_weight_EE_list",
               "cart_task_weight_Trunk", "joint_task_weight", "trunk_gain", "EE_gains", "dt"):
         setattr(dst, a, getattr(src, a))
+    for a in ("extra_rows", "compat_damper_off_by_one", "max_qp_iterations"):
+        if hasattr(src, a):
+            setattr(dst, a, getattr(src, a))
 
 
 def set_oracle_state(rm, q, mem, ref):
@@ -88,6 +91,13 @@ def oracle_step_one(rm, q, targets, mem, ref, imu=None, solve=True, tail=True):
         Ct = Clb = Cub = None
         Cm = np.zeros((0, A.shape[1]))
         Clb = Cub = None
+    extra = getattr(rm, "extra_rows", None)
+    if extra:                              # extension rows (NOT in the reference): coeff . J_frame(rf), appended to C
+        Ce, le, ue = oracle_extra_rows(rm, extra)
+        Cm = np.concatenate((Cm, Ce), axis=0)
+        Clb = le if Clb is None else np.concatenate((Clb, le))
+        Cub = ue if Cub is None else np.concatenate((Cub, ue))
+        Ct = Cm.T
     lb, ub = rm.velDamperJointConstraints()
     out.update(A=A, b=b, lb=lb, ub=ub, C=Cm, Clb=np.zeros(0) if Clb is None else Clb,
                Cub=np.zeros(0) if Cub is None else Cub, mem_out=get_oracle_mem(rm))
@@ -95,6 +105,7 @@ def oracle_step_one(rm, q, targets, mem, ref, imu=None, solve=True, tail=True):
     out["g"] = -A.T @ b
     if solve:
         qp = OracleQP(A, b, lb, ub, Ct, Clb, Cub, n_of_velocity_dimensions=rm.n_velocity_dimensions)
+        qp.max_iter = int(getattr(rm, "max_qp_iterations", 200))
         x = qp.solveQP()
         out.update(qdot=np.array(x), status=qp.result["status"], iters=qp.result["iters"], act=qp.result["act"])
         if tail:
@@ -105,6 +116,18 @@ def oracle_step_one(rm, q, targets, mem, ref, imu=None, solve=True, tail=True):
             out["q_next"] = np.array(rm.current_joint_config)
             out["q_integrated"] = full
     return out
+
+
+def oracle_extra_rows(rm, rows):
+    """The generic extension-row channel of WbcConfig (extra_frame / extra_rf / extra_coeff / extra_lo / extra_hi):
+    row = coeff . getFrameJacobian(hot frame slot, rf).  Slots 0..4 = EE frames, 5 = trunk."""
+    frames = rm.end_effector_index_list_frame + [rm.trunk_frame_index]
+    Ce, lo, hi = [], [], []
+    for slot, rf, coeff, l, h in rows:
+        J = opin.getFrameJacobian(rm.robot_model, rm.robot_data, frames[int(slot)], int(rf))
+        Ce.append(np.asarray(coeff, dtype=float) @ J)
+        lo.append(float(l)); hi.append(float(h))
+    return np.array(Ce), np.array(lo), np.array(hi)
 
 
 def oracle_step_batch(name, like, q, targets, mem, ref, imu=None, solve=True, tail=False):

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/wbc_b200.h but not exported"
     assert sorted(_cabi.EXPORTS) == declared, "the ctypes binding and the header disagree about the entry points"
-    assert lib.wbc_abi_version() == 1
+    assert lib.wbc_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (wbc_[a-z0-9_]+)", out))
     assert set(declared) <= exported
