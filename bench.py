@@ -4,14 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU loop (oracle port) on host cores
 
-A "step" is one pass of the hot path over one batch of synthetic states.  Default workload:
-A1+WX200, full step P3 (m = 62 task rows, nC = 16 constraint rows), 131072 states per GPU -- BASELINE.json
-configs[3] (the 1M-state sweep) sharded 8 ways, weak scaling: at --gpus 8 the job is exactly the 1M-state sweep.
-Inputs per GPU (q, targets, memory, references: 1128 B/state = 148 MB) exceed the 126 MB L2, so every timed
-step streams its inputs from HBM.  Rank 0 prints ONE JSON line.
+Workload of the headline numbers: A1+WX200, full step P3 (m = 62 task rows, nC = 16 constraint rows), 131072 states per
+GPU -- BASELINE.json configs[3] (the 1M-state sweep) sharded 8 ways, weak scaling: at --gpus 8 the job is exactly the
+1M-state sweep.  Inputs per GPU (q, targets, memory, references: 1128 B/state = 148 MB) exceed the 126 MB L2, so every
+pass streams its inputs from HBM.  A "step" is `passes_per_step` back-to-back passes of the hot path over the batch (one
+launch each; the count is chosen so that the K timed steps last >= 1 s and the clock samples describe the measurement
+itself), `value` = states x passes / time.  The `configs` block carries every other BASELINE configuration (config 2,
+config 3, bootstrap P1, the sim3.py HYBRID tick, config 5) at smaller timing budgets.  Rank 0 prints ONE JSON line.
 """
 import argparse
+import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -26,6 +30,11 @@ if ROOT not in sys.path:
 
 METRIC = "wbc_steps_per_s"
 UNIT = "steps/s"
+ALL_TASKS = dict(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True)
+GRIP_TASK = dict(Trunk=False, FR=False, FL=False, RR=False, RL=False, Grip=True)
+P2_CONS = dict(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+NO_CONS = dict(CoM=False, Trunk=False, FR=False, FL=False, RR=False, RL=False, Grip=False)
+TRUNK_ONLY = dict(CoM=False, Trunk=True, FR=False, FL=False, RR=False, RL=False, Grip=False)
 
 
 def algorithmic_flops(nv, njoints, m, nC, kbar, rot_support_cols):
@@ -42,53 +51,96 @@ def algorithmic_bytes(nq, nv):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / clock-event reasons of one GPU, sampled every 20 ms through NVML with a time stamp per sample
+    (fallback: an nvidia-smi poll, the B200_PROFILING.md recipe).  `summary(t0, t1)` only uses the samples taken inside
+    the wall-clock window of the timed region."""
+    BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
 
-    def __init__(self, gpu_index):
-        self.gpu_index = gpu_index
-        self.lines = []
+    def __init__(self, torch_device_index):
+        self.samples = []            # (t, sm_mhz, sm_max_mhz, power_w, reasons)
+        self.stop_flag = False
+        self.thread = None
+        self.source = None
+        self.idx = torch_device_index
         self.proc = None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].strip().isdigit() else self.idx
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            nv, h = self._nvml_handle()
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                     ("hw_power_brake", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), smax,
+                                             nv.nvmlDeviceGetPowerUsage(h) / 1e3, tuple(n for n, b in names if mask & b)))
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = "nvml, 20 ms"
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        fields = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, text=True, bufsize=1)
+
+            def loop():
+                for line in self.proc.stdout:
+                    p = [x.strip() for x in line.split(",")]
+                    try:
+                        self.samples.append((time.perf_counter(), float(p[1]), float(p[2]), float(p[3]),
+                                             tuple(n for n, v in zip(names, p[4:8]) if v.lower().startswith("active"))))
+                    except (ValueError, IndexError):
+                        continue
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = "nvidia-smi -lms 50"
+        except Exception:
+            self.source = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, p[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+
+    def summary(self, t0, t1):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        win = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not win:                                   # a region shorter than one poll: the nearest sample
+            win = sorted(self.samples, key=lambda s: abs(s[0] - 0.5 * (t0 + t1)))[:1]
+        reasons = sorted({r for s in win for r in s[4]})
+        return {"sm_mhz": float(np.median([s[1] for s in win])) if win else None,
+                "sm_min_mhz": float(min(s[1] for s in win)) if win else None,
+                "sm_max_mhz": float(max(s[2] for s in win)) if win else None,
+                "power_w_max": float(max(s[3] for s in win)) if win else None,
+                "samples": len(win), "window_s": t1 - t0, "source": self.source + ", samples inside the timed region only",
+                "reasons": reasons}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -101,8 +153,8 @@ class ClockSampler:
 def _p3_oracle(name, dt):
     from tests import helpers as H
     rm = H.make_oracle(name, dt=dt)
-    rm.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
-    rm.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+    rm.setTasks(Joint=True, **ALL_TASKS)
+    rm.setConstraints(**P2_CONS)
     return rm
 
 
@@ -246,93 +298,173 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args, per_gpu_states):
-    return {"workload": f"A1+{'WX200' if 'wx200' in args.robot else 'PX100'} full WBC step P3: FK + 6 frame Jacobians + "
-                        f"task stack (FR,FL,RR,RL,GRIP,Trunk,Joint) + velocity-damper bounds + 16 constraint rows + QP",
-            "robot": args.robot, "states_per_gpu": per_gpu_states, "sigma": args.sigma, "dt": args.dt,
-            "baseline_config": "configs[3] (1M-state sweep) sharded 8-way: 131072 states/GPU, weak scaling",
-            "l2": "inputs per GPU (1128 B/state) exceed the 126 MB L2; no explicit flush"}
+def workload_config(args, per_gpu_states, passes=None):
+    c = {"workload": f"A1+{'WX200' if 'wx200' in args.robot else 'PX100'} full WBC step P3: FK + 6 frame Jacobians + "
+                     f"task stack (FR,FL,RR,RL,GRIP,Trunk,Joint) + velocity-damper bounds + 16 constraint rows + QP",
+         "robot": args.robot, "states_per_gpu": per_gpu_states, "sigma": args.sigma, "dt": args.dt,
+         "baseline_config": "configs[3] (1M-state sweep) sharded 8-way: 131072 states/GPU, weak scaling",
+         "l2": "inputs per GPU (1128 B/state) exceed the 126 MB L2; no explicit flush"}
+    if passes is not None:
+        c["passes_per_step"] = passes
+    return c
 
 
 # ---------------------------------------------------------------------------------------------------------
 # GPU side
 # ---------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import wbc_b200
-    from wbc_b200 import synthetic, _cabi as cabi
-    import ctypes as C
+class Ctx:
+    """torch / distributed plumbing of one rank."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner) go to stderr
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        from wbc_b200 import sharding
+        self.torch, self.dist, self.sharding = torch, dist, sharding
+        self.rank, self.world, self.local_rank = sharding.world_info()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        return self.sharding.max_over_ranks(ms, self.dev)
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+def make_robot(ctx, name, n, dt, tasks, cons, joint, seed, sigma, extra=None, lo=0, n_global=None):
+    """RobotModel over this rank's contiguous shard [lo, lo + n) of the global synthetic batch."""
+    import wbc_b200
+    from wbc_b200 import synthetic
+    robot = wbc_b200.RobotModel(name, batch=n, device=ctx.dev, dt=dt)
+    robot.setTasks(Joint=joint, **tasks)
+    robot.setConstraints(**cons)
+    if extra:
+        robot.extra_rows = extra(robot.robot_model)
+    n_global = n_global or n
+    qg = synthetic.sample_configurations(robot.robot_model, n_global, seed)
+    ng = synthetic.sample_noise(n_global, seed, sigma)
+    targets = synthetic.load_batch(robot, qg[lo:lo + n], ng[lo:lo + n])
+    robot._pack_targets(targets[:, :15].reshape(n, 5, 3), targets[:, 15:18])
+    return robot, targets
+
+
+def stepper(robot, targets, advance=False):
+    """One pass = ONE kernel launch through the C ABI with pre-built argument structs (no torch kernels in between)."""
+    from wbc_b200 import _cabi as cabi
+    lib = cabi.load()
+    cfg = robot._config()
+    io = robot._io(targets=targets, qdot=robot.qdot, status=robot.last_status, iters=robot.last_iters)
+    sp = C.c_void_p(ctx_stream())
+    N = robot.N
+
+    def one():
+        cabi.check(lib.wbc_step(robot._model, C.byref(cfg), C.byref(io), N, sp))
+    return one
+
+
+def ctx_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def time_passes(ctx, one, min_seconds, warmup=3, passes=None):
+    """Device-timed back-to-back passes: (ms per pass max over ranks, passes)."""
+    for _ in range(warmup):
+        one()
+    ctx.barrier()
+    if passes is None:
+        e0, e1 = ctx.event(), ctx.event()
+        e0.record(); one(); e1.record()
+        ctx.torch.cuda.synchronize()
+        passes = max(3, int(math.ceil(min_seconds * 1e3 / max(ctx.max_ms(e0.elapsed_time(e1)), 1e-3))))
+        ctx.barrier()
+    e0, e1 = ctx.event(), ctx.event()
+    e0.record()
+    for _ in range(passes):
+        one()
+    e1.record()
+    ctx.barrier()
+    return ctx.max_ms(e0.elapsed_time(e1)) / passes, passes
+
+
+def config_line(ctx, label, name, n, dt, tasks, cons, joint, seed, sigma, budget_s, extra=None, what=""):
+    """One BASELINE configuration at a small timing budget: steps/s, ms per launch, mean QP iterations, geometry."""
+    robot, targets = make_robot(ctx, name, n, dt, tasks, cons, joint, seed + 1000 * ctx.rank, sigma, extra=extra)
+    one = stepper(robot, targets)
+    ms, passes = time_passes(ctx, one, budget_s)
+    st = robot.last_status
+    m, nc = robot._rows(robot._config())
+    return {"config": label, "what": what, "robot": name, "states_per_gpu": n, "task_rows": m, "constraint_rows": nc,
+            "steps_per_s": n * ctx.world / (ms * 1e-3), "ms_per_launch": ms, "launches_timed": passes,
+            "mean_qp_iterations": float(robot.last_iters.double().mean().item()),
+            "solved_fraction": float((st == 0).double().mean().item())}
+
+
+def run_ours(args):
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner, at communicator
+    # creation) go to stderr -- on every rank, and before the process group exists
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx()
+    torch, dist = ctx.torch, ctx.dist
+    import wbc_b200
+    from wbc_b200 import synthetic, sharding, _cabi as cabi
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
 
     n_local = args.states
     n_global = n_local * world
-    robot = wbc_b200.RobotModel(args.robot, batch=n_local, device=dev, dt=args.dt)
-    robot.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
-    robot.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+    lo, hi = sharding.shard_range(n_global, rank, world)             # this rank's contiguous shard of the global batch
+    assert hi - lo == n_local
+    robot, targets = make_robot(ctx, args.robot, n_local, args.dt, ALL_TASKS, P2_CONS, True, args.seed, args.sigma, lo=lo,
+                                n_global=n_global)
     table = robot.robot_model
-    # global arrays, then this rank's contiguous shard (results independent of the rank count)
-    qg = synthetic.sample_configurations(table, n_global, args.seed)
-    ng = synthetic.sample_noise(n_global, args.seed, args.sigma)
-    lo, hi = rank * n_local, (rank + 1) * n_local
-    targets = synthetic.load_batch(robot, qg[lo:hi], ng[lo:hi])
-    del qg, ng
-    ee_t, tr_t = targets[:, :15].reshape(n_local, 5, 3), targets[:, 15:18]
-    robot._pack_targets(ee_t, tr_t)
-    mem0 = robot._mem.clone()
+    mem0, ref0, q0 = robot._mem.clone(), robot._ref.clone(), robot.current_joint_config.clone()
+    one_pass = stepper(robot, targets)           # q, targets, task memory, references in; qdot, status, iters out: 1344 B/state
 
-    def one_step():
-        # q, targets, task memory, references in; qdot, status, iters out: the 1344 B/state of SURVEY 8d (the active-set
-        # masks, an extension the reference does not return, are left to the verification pass below)
-        robot.step(ee_t, tr_t, advance=False, report_active_set=False)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- headline: K steps of R passes each, >= 1 s in total, clocks sampled while it runs -------------------
     for _ in range(max(args.warmup, 3)):
-        one_step()
-    barrier()
+        one_pass()
+    ctx.barrier()
+    e0, e1 = ctx.event(), ctx.event()
+    e0.record(); one_pass(); e1.record()
+    torch.cuda.synchronize()
+    t_pass_ms = ctx.max_ms(e0.elapsed_time(e1))
+    passes = args.passes if args.passes > 0 else max(1, int(math.ceil(args.min_seconds * 1e3 / (args.steps * t_pass_ms))))
+
     def timed_region():
-        """K steps between barriers, CUDA events on the launching stream; nvidia-smi clocks sampled while it runs
-        (the sampler keeps the GPU under the same load for >= 0.5 s so that a 100 ms poll sees it)."""
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(ctx.local_rank)
         if rank == 0:
             sampler.start()
-            t_load = time.perf_counter()
-            while time.perf_counter() - t_load < 0.5:          # untimed: same kernel, lets the clock samples land under load
-                one_step()
-                torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
-        t_wall0 = time.perf_counter()
+            time.sleep(0.05)
+        evs = [(ctx.event(), ctx.event()) for _ in range(args.steps)]
+        ctx.barrier()
+        w0 = time.perf_counter()
         for k in range(args.steps):
             evs[k][0].record()
-            one_step()
+            for _ in range(passes):
+                one_pass()
             evs[k][1].record()
-        barrier()
-        wall_ = time.perf_counter() - t_wall0
-        clocks_ = sampler.stop() if rank == 0 else None
-        return [a.elapsed_time(b) for a, b in evs], evs[0][0].elapsed_time(evs[-1][1]), wall_, clocks_
+        ctx.barrier()
+        w1 = time.perf_counter()
+        clocks_ = None
+        if rank == 0:
+            sampler.stop()
+            clocks_ = sampler.summary(w0, w1)
+        return [a.elapsed_time(b) for a, b in evs], evs[0][0].elapsed_time(evs[-1][1]), w1 - w0, clocks_
 
     per_step_ms, total_ms, wall, clocks = timed_region()
     remeasured = False
-    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    flag = torch.tensor([1.0 if (rank == 0 and clocks and bad & set(clocks.get("reasons", []))) else 0.0], device=dev)
+    flag = torch.tensor([1.0 if (rank == 0 and clocks and set(ClockSampler.BAD) & set(clocks.get("reasons", []))) else 0.0], device=dev)
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)
     if flag.item() > 0:                                        # throttled: cool down and measure once more
@@ -341,66 +473,124 @@ def run_ours(args):
         remeasured = True
     if rank == 0 and clocks is not None:
         clocks["remeasured"] = remeasured
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = n_global * args.steps / (total_ms_max * 1e-3)
+    total_ms_max = ctx.max_ms(total_ms)
+    value = n_global * args.steps * passes / (total_ms_max * 1e-3)
     status_ok = bool((robot.last_status == 0).all().item())
     kbar = float(robot.last_iters.double().mean().item())
-    assert torch.equal(robot._mem, mem0), "advance=False must leave the task memory untouched"
+    qdot_open = robot.qdot.clone()
+    assert torch.equal(robot._mem, mem0), "the open-loop pass must leave the task memory untouched"
 
-    # ---- end-to-end leg: host buffers in, host buffers out, through the public API -------------------
+    # ---- end to end: the runWBC tick through RobotModel.step_host -> wbc_step_host with HOST buffers ----------
+    nq, nv = table.nq, table.nv
     pin = dict(pin_memory=True)
-    host_in = {"q": robot.current_joint_config.cpu().pin_memory(), "targets": targets.cpu().pin_memory(),
-               "mem": robot._mem.cpu().pin_memory(), "ref": robot._ref.cpu().pin_memory()}
-    host_out = {"qdot": torch.empty(n_local, table.nv, dtype=torch.float64, **pin),
-                "status": torch.empty(n_local, dtype=torch.int32, **pin),
-                "iters": torch.empty(n_local, dtype=torch.int32, **pin)}
-    e2e_steps = max(3, min(args.steps, 10))
+    RING = 8                          # distinct pinned input buffers used round-robin: 8 x 23 MB > L2, and targets do move
+    gen = torch.Generator(device="cpu"); gen.manual_seed(args.seed + 17 + rank)
+    t_cpu = targets.cpu()
+    walk = torch.randn(RING, n_local, 18, dtype=torch.float64, generator=gen).mul_(1e-4).cumsum(0)
+    walk[:, :, :12] = 0.0                                      # feet stay planted (their rows are equalities); gripper / trunk targets wander
+    imu0 = q0[:, 3:7].cpu()
+    ring64 = [{"targets": (t_cpu + walk[r]).pin_memory(), "imu": imu0.clone().pin_memory()} for r in range(RING)]
 
-    E2E_CHUNKS = int(os.environ.get("WBC_E2E_CHUNKS", "0"))     # 0: zero-copy from / to pinned host memory; n >= 1: n staged slices
-    def e2e_leg(resident_state):
+    def host_out(dtype, closed):
+        o = {"status": torch.empty(n_local, dtype=torch.int32, **pin)}
+        if closed:        # what runWBC returns (the joint position targets) + the solver status; the iteration counts stay on the device
+            o["joint_targets"] = torch.empty(n_local, nq - 7, dtype=dtype, **pin)
+        else:
+            o["qdot"] = torch.empty(n_local, nv, dtype=dtype, **pin)
+            o["iters"] = torch.empty(n_local, dtype=torch.int32, **pin)
+        return o
+
+    def reset_state():
+        # (a fresh tensor, not copy_: rollout() / step(advance=True) rebind current_joint_config, and the pre-built argument
+        #  structs of `one_pass` hold raw pointers -- they are rebuilt below before the kernel is launched through them again)
+        robot.current_joint_config = q0.clone(); robot._mem.copy_(mem0); robot._ref.copy_(ref0)
+
+    cfg_tick = robot._config()        # the controller's settings do not change from tick to tick: marshalled once
+
+    def e2e_closed(chunks, ring, out, steps, delta=False, warm=3):
+        """`steps` consecutive closed-loop ticks; every tick reads its inputs from host memory and writes its results there."""
+        reset_state()
+        for k in range(warm):
+            robot.step_host(ring[k % RING], out, chunks=chunks, closed_loop=True, delta_inputs=delta, cfg=cfg_tick)
+        ctx.barrier()
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        for k in range(steps):
+            h2d_, d2h_ = robot.step_host(ring[(warm + k) % RING], out, chunks=chunks, closed_loop=True, delta_inputs=delta,
+                                         cfg=cfg_tick)
+        b.record()
+        ctx.barrier()
+        ms = ctx.max_ms(a.elapsed_time(b))
+        solved = float((out["status"] == 0).double().mean().item())
+        return n_global * steps / (ms * 1e-3), h2d_, d2h_, solved, ms / steps
+
+    e2e_steps = max(args.steps, int(math.ceil(args.e2e_seconds * 1e3 / max(t_pass_ms * 1.3, 1e-3))))
+    out64 = host_out(torch.float64, True)
+    # which host path: zero-copy (the kernel reads / writes pinned host memory itself) or staged slices -- measured, not guessed
+    variants = {}
+    forced = os.environ.get("WBC_E2E_CHUNKS")
+    cand = [int(forced)] if forced is not None else [0, 4, 8]
+    for ch in cand:
+        v, _, _, _, _ = e2e_closed(ch, ring64, out64, max(5, e2e_steps // 8))
+        variants[ch] = v
+    best = max(variants, key=variants.get)
+    e2e_value, h2d, d2h, e2e_solved, e2e_ms = e2e_closed(best, ring64, out64, e2e_steps)
+    # the closed-loop host tick lands where the device-resident closed loop lands
+    reset_state()
+    chk_steps = 3
+    trj = torch.stack([ring64[k % RING]["targets"] for k in range(chk_steps)]).to(dev)
+    imu_trj = torch.stack([ring64[k % RING]["imu"] for k in range(chk_steps)]).to(dev)
+    robot.rollout(trj[:, :, :15].reshape(chk_steps, n_local, 5, 3), trj[:, :, 15:18], imu_quat_traj=imu_trj)
+    q_roll = robot.current_joint_config.clone()
+    reset_state()
+    for k in range(chk_steps):
+        robot.step_host(ring64[k % RING], out64, chunks=best, closed_loop=True)
+    torch.cuda.synchronize()
+    e2e_ok = bool(torch.equal(robot.current_joint_config, q_roll)) and bool(torch.equal(out64["joint_targets"], q_roll[:, 7:].cpu()))
+
+    # second legs: the FP32 I/O mode (increments, float32) and the two open-loop calls of round 1
+    reset_state()
+    enc = wbc_b200.HostDeltaEncoder(robot)
+    ring32 = []
+    for r in range(RING):            # consecutive increments along the same ring (the encoder mirrors the device state)
+        dt32, di32 = enc.encode(ring64[r]["targets"], ring64[r]["imu"])
+        ring32.append({"targets": dt32.pin_memory(), "imu": di32.pin_memory()})
+    # (the ring is replayed: the increments of lap 2 restart from ring[0], so lap boundaries jump back -- harmless for timing)
+    out32 = host_out(torch.float32, True)
+    f32_value, h2d32, d2h32, f32_solved, _ = e2e_closed(best, ring32, out32, max(5, e2e_steps // 4), delta=True)
+
+    def e2e_open(resident, steps):
+        reset_state()
+        hin = {"q": q0.cpu().pin_memory(), "targets": t_cpu.pin_memory(), "mem": mem0.cpu().pin_memory(), "ref": ref0.cpu().pin_memory()}
+        out = host_out(torch.float64, False)
         for _ in range(3):
-            h2d_, d2h_ = robot.step_host(host_in, host_out, chunks=E2E_CHUNKS, resident_state=resident_state)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(e2e_steps):
-            robot.step_host(host_in, host_out, chunks=E2E_CHUNKS, resident_state=resident_state)
-        e1.record()
-        barrier()
-        t_ = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        ok_ = bool((host_out["status"] == 0).all().item())
-        return n_global * e2e_steps / (float(t_.item()) * 1e-3), h2d_, d2h_, ok_
-
-    # headline: the per-tick inputs (q, targets) come from the host every step, the controller state (task memory,
-    # per-robot references: attributes of the reference's RobotModel object) is resident; second leg: everything
-    # travels (PCIe-bound: 1128 B in per state)
-    e2e_value, h2d, d2h, e2e_ok = e2e_leg(True)
-    e2e_all_value, h2d_all, d2h_all, ok_all = e2e_leg(False)
-    e2e_ok = e2e_ok and ok_all
+            h2d_, d2h_ = robot.step_host(hin, out, chunks=0, resident_state=resident)
+        ctx.barrier()
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        for _ in range(steps):
+            robot.step_host(hin, out, chunks=0, resident_state=resident, cfg=cfg_tick)
+        b.record()
+        ctx.barrier()
+        ms = ctx.max_ms(a.elapsed_time(b))
+        same = bool(torch.equal(out["qdot"], qdot_open.cpu()))
+        return n_global * steps / (ms * 1e-3), h2d_, d2h_, same
+    open_res = e2e_open(True, max(5, e2e_steps // 8))
+    open_all = e2e_open(False, max(5, e2e_steps // 16))
+    e2e_ok = e2e_ok and open_res[3] and open_all[3]
+    reset_state()
 
     # ---- single-state latency: one robot, one launch (the reference's own use case: a 500 Hz control tick) ----
     lat_us = None
     if rank == 0:
-        one = wbc_b200.RobotModel(args.robot, batch=1, device=dev, dt=args.dt)
-        one.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
-        one.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
-        one.current_joint_config.copy_(robot.current_joint_config[:1]); one._mem.copy_(mem0[:1]); one._ref.copy_(robot._ref[:1])
-        t1 = targets[:1].clone()
-        cfg1 = one._config()
-        io1 = one._io(targets=t1, qdot=one.qdot, status=one.last_status, iters=one.last_iters)
-        lib = cabi.load()
-        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        one, t1 = make_robot(ctx, args.robot, 1, args.dt, ALL_TASKS, P2_CONS, True, args.seed, args.sigma)
+        f1 = stepper(one, t1)
         for _ in range(20):
-            lib.wbc_step(one._model, C.byref(cfg1), C.byref(io1), 1, sp)
+            f1()
         torch.cuda.synchronize()
-        evl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+        evl = [(ctx.event(), ctx.event()) for _ in range(50)]
         for a_, b_ in evl:
-            a_.record(); lib.wbc_step(one._model, C.byref(cfg1), C.byref(io1), 1, sp); b_.record()
+            a_.record(); f1(); b_.record()
         torch.cuda.synchronize()
         lat_us = float(np.median([a_.elapsed_time(b_) for a_, b_ in evl]) * 1e3)
 
@@ -409,7 +599,7 @@ def run_ours(args):
     if rank == 0:
         robot.frameJacobians(cabi.RF_LOCAL_WORLD_ALIGNED)
         torch.cuda.synchronize()
-        ef = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        ef = [(ctx.event(), ctx.event()) for _ in range(5)]
         for a_, b_ in ef:
             a_.record(); robot.frameJacobians(cabi.RF_LOCAL_WORLD_ALIGNED); b_.record()
         torch.cuda.synchronize()
@@ -417,42 +607,35 @@ def run_ours(args):
         fkj_bytes = (6 * (12 + 6 * table.nv) * 8 + 8 * table.nq) * n_local
         fkj = {"ms": fkj_ms, "bytes_per_state": 6 * (12 + 6 * table.nv) * 8 + 8 * table.nq, "gbs": fkj_bytes / fkj_ms / 1e6}
 
-    # ---- BASELINE config 5 (optional): closed-loop horizon, K ticks, state resident on the device -----------------
-    rollout_line = None
-    if args.rollout > 0:
-        K = args.rollout
-        rr = wbc_b200.RobotModel(args.robot, batch=n_local, device=dev, dt=args.dt)
-        rr.setTasks(Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=True, Joint=True)
-        rr.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
-        rr.current_joint_config = robot.current_joint_config.clone(); rr._mem.copy_(mem0); rr._ref.copy_(robot._ref)
-        # feet stay planted (their rows are equalities); the gripper and trunk targets wander: per-robot random walk
-        gen = torch.Generator(device=dev); gen.manual_seed(args.seed + 5)
-        drift = torch.zeros(K, n_local, 18, dtype=torch.float64, device=dev)
-        drift[:, :, 12:18] = torch.randn(K, n_local, 6, dtype=torch.float64, device=dev, generator=gen).mul_(1e-4).cumsum(0)
-        traj = targets[None] + drift
-        ee_tr, tr_tr = traj[:, :, :15].reshape(K, n_local, 5, 3), traj[:, :, 15:18]
-        rr.rollout(ee_tr[:2], tr_tr[:2])                                   # warm-up
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record(); rr.rollout(ee_tr, tr_tr); r1.record()
-        barrier()
-        tr_ms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tr_ms, op=dist.ReduceOp.MAX)
-        rollout_line = {"ticks": K, "robots": n_global, "steps_per_s": n_global * K / (float(tr_ms.item()) * 1e-3),
-                        "ms_per_tick": float(tr_ms.item()) / K, "solved_fraction_last_tick": float((rr.last_status == 0).double().mean().item()),
-                        "mean_qp_iterations_last_tick": float(rr.last_iters.double().mean().item())}
+    # ---- every other BASELINE configuration, at small timing budgets ----------------------------------------
+    configs = []
+    if not args.no_configs:
+        b = args.config_seconds
+        if world == 1:
+            configs.append(config_line(ctx, "configs[1]", "a1_px100_pin_ver", 4096, args.dt, ALL_TASKS, P2_CONS, True, 20260001, 5e-3, b,
+                                       what="A1+PX100 batched WBC step, 4096 random states, FP64 (every state compared with the CPU loop in tests/)"))
+            configs.append(config_line(ctx, "configs[2]", "a1_wx200", 65536, args.dt, ALL_TASKS, TRUNK_ONLY, True, 20260003, 5e-3, b,
+                                       extra=synthetic.config3_rows,
+                                       what="A1+WX200 with friction-pyramid + torque-limit proxy rows (27 constraint rows, general front, full-width solver), 65536 states"))
+            configs.append(config_line(ctx, "P1 bootstrap", "a1_wx200", n_local, args.dt, ALL_TASKS, NO_CONS, True, 20260004, 5e-3, b,
+                                       what="setInitialState tick (Robot_Wrapper4.py:278-325): full task stack, bounds-only QP"))
+            configs.append(config_line(ctx, "P2 sim3 tick (HYBRID)", "a1_px100_pin_ver", 32768, args.dt, GRIP_TASK, P2_CONS, "HYBRID", 20260005, 5e-4, b,
+                                       what="what sim3.py:145-148 runs: gripper task + HYBRID joint task (12 finite-difference FK passes per tick) + trunk / feet constraints"))
+            configs.append(config_line(ctx, "P3 stress", "a1_wx200", n_local, args.dt, ALL_TASKS, P2_CONS, True, 20260006, 5e-3, b,
+                                       what="the headline step with 10x the target noise: bounds and the trunk box bind"))
+        configs.append(rollout_line(ctx, args, 16384, 100))
 
     # ---- verification gather (off the timed path): NCCL all_gather of solutions / status -------------
-    verified = status_ok and e2e_ok
-    checksum = float(robot.qdot.double().abs().sum().item())
-    if world > 1:
-        gathered = torch.empty(world * n_local, table.nv, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(gathered, robot.qdot.contiguous())
-        st = torch.empty(world * n_local, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(st, robot.last_status.contiguous())
-        verified = verified and bool((st == 0).all().item()) and bool(torch.isfinite(gathered).all().item())
-        checksum = float(gathered.abs().sum().item())
+    reset_state()
+    one_pass = stepper(robot, targets)
+    one_pass()                                                 # the open-loop pass once more, after all the legs above
+    torch.cuda.synchronize()
+    same_again = bool(torch.equal(robot.qdot, qdot_open))
+    gathered = sharding.gather_states(robot.qdot.contiguous(), n_global)
+    st_all = sharding.gather_states(robot.last_status.contiguous(), n_global)
+    verified = (status_ok and e2e_ok and same_again and bool((st_all == 0).all().item())
+                and bool(torch.isfinite(gathered).all().item()))
+    checksum = float(gathered.abs().sum().item())
 
     if rank == 0:
         # ---- FP64 roofline denominator: measured DFMA peak (MEASURED_PEAKS.json has none) ---------------
@@ -468,39 +651,58 @@ def run_ours(args):
         rot_cols = 4 * 6 + (3 + 5) + 3
         f_fkj, f_asm, f_qp = algorithmic_flops(table.nv, table.njoints, m_rows, nC, kbar, rot_cols)
         f_step = f_fkj + f_asm + f_qp
-        kern_s = (total_ms / args.steps) * 1e-3            # one kernel per step: average launch duration (CUDA events)
+        kern_s = (total_ms / (args.steps * passes)) * 1e-3     # one kernel per pass: average launch duration (CUDA events)
         ach_tflops = f_step * n_local / kern_s / 1e12
         bytes_state = algorithmic_bytes(table.nq, table.nv)
         info = robot.launch_info()
-        traffic = None                                     # measured DRAM bytes of one launch (ncu), scaled to this launch
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            traffic = tr["bytes_per_state"] * n_local
-        except Exception:
-            pass
+        traffic, traffic_src = None, None                      # measured DRAM bytes of one launch (ncu), scaled to this launch
+        for fn in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                traffic, traffic_src = tr["bytes_per_state"] * n_local, fn
+                break
+            except Exception:
+                pass
+        pcie = lambda v, bytes_: v / world * bytes_ / n_local / 1e9        # GB/s per GPU
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_local),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_local, passes),
+            "ms_per_launch": total_ms_max / (args.steps * passes),
             "p50_step_us": float(np.median(per_step_ms) * 1e3),
-            "ns_per_state": 1e6 * total_ms_max / args.steps / n_global * world,
+            "ns_per_state": 1e6 * total_ms_max / (args.steps * passes) / n_global * world,
             "p50_single_state_step_us": lat_us,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "RobotModel.step_host(resident_state=True) -> wbc_step_host (C ABI): q and targets from "
-                                                  "pinned host buffers every step, qdot / status / iters back to the host; task memory "
-                                                  "and per-robot references stay in the controller object (device), as the reference "
-                                                  "keeps them as attributes; " + ("zero-copy: the kernel reads / writes the pinned host "
-                                                  "buffers over PCIe itself, one launch" if E2E_CHUNKS <= 0 else
-                                                  f"{E2E_CHUNKS} staged slices pipelined over 3 streams"),
-                    "gpu_launches_per_step": 1 if E2E_CHUNKS <= 0 else E2E_CHUNKS,
-                    "all_inputs_from_host": {"value": e2e_all_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all,
-                                             "d2h_bytes_per_step": d2h_all,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms, "solved_fraction_last_tick": e2e_solved,
+                    "api": "RobotModel.step_host(closed_loop=True) -> wbc_step_host (C ABI): the runWBC tick "
+                           "(Robot_Wrapper4.py:1330-1412) for a caller holding host arrays -- every step the IMU quaternion and the "
+                           "six targets are read from pinned HOST buffers (a ring of 8 distinct buffers, > L2) and the joint "
+                           "position targets + status + iterations are written to pinned HOST buffers; configuration, task "
+                           "memory and references are the controller's state: resident on the device and ADVANCED IN PLACE "
+                           "every step (prev targets / reference rotations, integrate, IMU feedback, base re-estimate), as "
+                           "runWBC mutates its object.  " +
+                           ("zero-copy: the kernel reads / writes the pinned host buffers over PCIe itself, one launch per step"
+                            if best <= 0 else f"{best} staged slices pipelined over 3 streams (cudaMemcpyAsync H2D, kernel, D2H)"),
+                    "host_path": "zero_copy" if best <= 0 else f"staged_{best}",
+                    "host_path_candidates_steps_per_s": {("zero_copy" if k <= 0 else f"staged_{k}"): v for k, v in variants.items()},
+                    "gpu_launches_per_step": 1 if best <= 0 else best,
+                    "pcie_gbs_per_gpu": {"h2d": pcie(e2e_value, h2d), "d2h": pcie(e2e_value, d2h)},
+                    "equals_device_rollout": e2e_ok,
+                    "fp32_io": {"value": f32_value, "unit": UNIT, "dtype": "f32 host I/O (increment inputs), f64 arithmetic",
+                                "h2d_bytes_per_step": h2d32, "d2h_bytes_per_step": d2h32, "solved_fraction_last_tick": f32_solved,
+                                "note": "optional FP32 I/O mode (WBC_HOST_F32 + WBC_HOST_FLAG_DELTA_INPUTS): agrees with the "
+                                        "float64 call to < 1e-4 (tests/test_gpu_surface.py); reported beside, not instead of, f64"},
+                    "open_loop_resident_state": {"value": open_res[0], "unit": UNIT, "h2d_bytes_per_step": open_res[1],
+                                                 "d2h_bytes_per_step": open_res[2],
+                                                 "note": "round-1 headline: q + targets in, qdot out, nothing advanced on the device"},
+                    "all_inputs_from_host": {"value": open_all[0], "unit": UNIT, "h2d_bytes_per_step": open_all[1],
+                                             "d2h_bytes_per_step": open_all[2],
                                              "note": "q, targets, task memory and references all cross PCIe every step (PCIe-bound)"}},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * passes,
             "clocks": clocks,
             "roofline": {"bound": "fp64_fma", "achieved": ach_tflops, "peak": peak.value / 1e12, "unit": "TFLOP/s",
                          "frac": ach_tflops / (peak.value / 1e12), "traffic": traffic,
-                         "traffic_source": "profiles/r1_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of "
+                         "traffic_source": f"profiles/{traffic_src}: ncu dram__bytes_read.sum + dram__bytes_write.sum of "
                                            "wbc_step_kernel at 131072 states, per state x states of this launch",
                          "peak_source": "measured in this run: DFMA-saturating microkernel (wbc_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
@@ -515,27 +717,60 @@ def run_ours(args):
             "roofline_fk_jac": {"bound": "hbm", "kernel": "wbc_fk_jac_kernel (6 frames, LOCAL_WORLD_ALIGNED, placements + Jacobians)",
                                 "achieved": fkj["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": fkj["gbs"] / hbm_peak,
                                 "bytes_per_state": fkj["bytes_per_state"], "ms": fkj["ms"]},
-            "rollout": rollout_line,
+            "configs": configs,
             "mean_qp_iterations": kbar, "verified": verified, "checksum_abs_qdot": checksum,
             "launch": info, "wall_s_timed_region": wall,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             n_cpu = min(n_local, 4096)                    # the first states of the very batch the GPU just solved
-            arrays = (robot.current_joint_config[:n_cpu].cpu().numpy(), targets[:n_cpu].cpu().numpy(),
-                      mem0[:n_cpu].cpu().numpy(), robot._ref[:n_cpu].cpu().numpy())
+            arrays = (q0[:n_cpu].cpu().numpy(), targets[:n_cpu].cpu().numpy(), mem0[:n_cpu].cpu().numpy(), ref0[:n_cpu].cpu().numpy())
             line["cpu_baseline"] = cpu_baseline_block(args.robot, arrays, args.dt, cores, 2.0, py_states=cores * 8)
             # the C port doubles as a checker: same states, same answers
             from oracle import c_port
             ts, table_c = c_port.table_struct(args.robot)
             chk = c_port.step(ts, c_port.config_struct(_p3_oracle(args.robot, args.dt), table_c), *arrays, args.dt, nthreads=1)
-            line["max_abs_diff_vs_cpu_oracle"] = float(np.abs(chk["qdot"] - robot.qdot[:n_cpu].cpu().numpy()).max())
+            line["max_abs_diff_vs_cpu_oracle"] = float(np.abs(chk["qdot"] - qdot_open[:n_cpu].cpu().numpy()).max())
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def rollout_line(ctx, args, robots_per_gpu, K):
+    """BASELINE config 5: closed-loop horizon -- K Euler-integrated ticks of `robots_per_gpu` robots per GPU, state resident on
+    the device, one fused launch per tick (wbc_rollout)."""
+    torch = ctx.torch
+    rr, targets = make_robot(ctx, args.robot, robots_per_gpu, args.dt, ALL_TASKS, P2_CONS, True, args.seed + 50 + 1000 * ctx.rank, args.sigma)
+    if args.rollout_max_iter > 0:
+        rr.max_qp_iterations = args.rollout_max_iter
+    q0, mem0 = rr.current_joint_config.clone(), rr._mem.clone()
+    n = robots_per_gpu
+    # feet stay planted (their rows are equalities); the gripper and trunk targets wander: per-robot random walk
+    gen = torch.Generator(device=ctx.dev); gen.manual_seed(args.seed + 5 + ctx.rank)
+    drift = torch.zeros(K, n, 18, dtype=torch.float64, device=ctx.dev)
+    drift[:, :, 12:18] = torch.randn(K, n, 6, dtype=torch.float64, device=ctx.dev, generator=gen).mul_(1e-4).cumsum(0)
+    traj = targets[None] + drift
+    ee_tr, tr_tr = traj[:, :, :15].reshape(K, n, 5, 3), traj[:, :, 15:18]
+    rr.rollout(ee_tr[:2], tr_tr[:2])                                   # warm-up
+    best = None
+    for _ in range(3):
+        rr.current_joint_config = q0.clone(); rr._mem.copy_(mem0)
+        ctx.barrier()
+        r0, r1 = ctx.event(), ctx.event()
+        r0.record(); rr.rollout(ee_tr, tr_tr); r1.record()
+        ctx.barrier()
+        ms = ctx.max_ms(r0.elapsed_time(r1))
+        best = ms if best is None else min(best, ms)
+    return {"config": "configs[4]", "what": f"closed-loop rollout: {K} Euler-integrated WBC ticks over {n} robots per GPU, task memory and "
+                                            "configuration advanced in place on the device, one fused launch per tick",
+            "robot": args.robot, "states_per_gpu": n, "ticks": K, "robots": n * ctx.world,
+            "steps_per_s": n * ctx.world * K / (best * 1e-3), "ms_per_tick": best / K,
+            "qp_iteration_cap": rr.max_qp_iterations,
+            "solved_fraction_last_tick": float((rr.last_status == 0).double().mean().item()),
+            "mean_qp_iterations_last_tick": float(rr.last_iters.double().mean().item())}
 
 
 def main():
@@ -549,8 +784,13 @@ def main():
     ap.add_argument("--sigma", type=float, default=5e-4)
     ap.add_argument("--dt", type=float, default=0.002)
     ap.add_argument("--seed", type=int, default=20260003)
+    ap.add_argument("--passes", type=int, default=0, help="passes over the batch per step (0: as many as make the K steps last --min-seconds)")
+    ap.add_argument("--min-seconds", type=float, default=1.2, help="length of the timed region")
+    ap.add_argument("--e2e-seconds", type=float, default=0.6, help="length of the end-to-end timed region")
+    ap.add_argument("--config-seconds", type=float, default=0.25, help="timing budget of each entry of the `configs` block")
+    ap.add_argument("--rollout-max-iter", type=int, default=0, help="QP iteration cap of the config-5 rollout (0: the default 200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rollout", type=int, default=0, help="BASELINE config 5: closed-loop horizon of K ticks (extra line on stderr)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configurations)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -286,7 +286,10 @@ class RobotModel:
         return m
 
     def _config(self, task_mask=None, constraint_mask=None):
+        """The controller's settings as the WbcConfig struct that travels with every call (bulk copies through NumPy
+        views of the ctypes arrays: this runs once per tick)."""
         c = cabi.WbcConfig()
+        view = np.ctypeslib.as_array
         c.task_mask = self._task_mask() if task_mask is None else task_mask
         j = self.task_active_Joint
         c.joint_mode = _JOINT_MODES.get(j if isinstance(j, str) else True, cabi.JOINT_ZERO)
@@ -295,25 +298,20 @@ class RobotModel:
         c.gripper_joint_id = self.end_effector_index_list_joint[4]
         c.arm_base_id = self.arm_base_id
         c.max_iter = int(self.max_qp_iterations)
-        for i in range(5):
-            W = np.asarray(self.EE_weight[i], dtype=float).reshape(-1)
-            G = np.asarray(self.EE_gains[i], dtype=float)[0:3, 0:3].reshape(-1)          # EE_gains[frame_index] (:908)
-            for k in range(36):
-                c.ee_weight[i][k] = W[k]
-            for k in range(9):
-                c.ee_gain_pos[i][k] = G[k]
-            c.cart_task_weight[i] = float(self.cart_task_weight_EE_list[i])
-        W = np.asarray(self.trunk_weight, dtype=float).reshape(-1)
-        for k in range(36):
-            c.trunk_weight[k] = W[k]
-        c.cart_task_weight[5] = float(self.cart_task_weight_Trunk)
+        view(c.ee_weight)[:] = np.asarray(self.EE_weight, dtype=np.float64).reshape(5, 36)
+        # EE_gains[frame_index] (:908): the list is built FL, FR, RL, RR, GRIP (:125) -- indexed as given (quirk D.8)
+        view(c.ee_gain_pos)[:] = np.asarray(self.EE_gains, dtype=np.float64)[:, 0:3, 0:3].reshape(5, 9)
+        view(c.trunk_weight)[:] = np.asarray(self.trunk_weight, dtype=np.float64).reshape(36)
+        ctw = view(c.cart_task_weight)
+        ctw[:5] = np.asarray(self.cart_task_weight_EE_list, dtype=np.float64)
+        ctw[5] = float(self.cart_task_weight_Trunk)
         c.joint_task_weight = float(self.joint_task_weight)
-        G = np.asarray(self.trunk_gain, dtype=float)
-        for k in range(9):
-            c.trunk_gain_pos[k] = G[0:3, 0:3].reshape(-1)[k]
-        for k in range(3):
-            c.trunk_gain_ori[k] = G[3 + k, 3 + k]
+        G = np.asarray(self.trunk_gain, dtype=np.float64)
+        view(c.trunk_gain_pos)[:] = G[0:3, 0:3].reshape(9)
+        view(c.trunk_gain_ori)[:] = np.diagonal(G)[3:6]
         c.damper_coef, c.damper_qi, c.damper_qs = self.damper
+        if len(self.extra_rows) > cabi.MAX_EXTRA:
+            raise ValueError(f"at most {cabi.MAX_EXTRA} extension rows")
         c.n_extra_rows = len(self.extra_rows)
         for e, (slot, rf, coeff, lo, hi) in enumerate(self.extra_rows):
             c.extra_frame[e], c.extra_rf[e], c.extra_lo[e], c.extra_hi[e] = int(slot), int(rf), float(lo), float(hi)
@@ -658,7 +656,7 @@ class RobotModel:
             self.current_joint_config = q_next
         return self.qdot
 
-    def step_host(self, host_in, host_out, chunks=0, resident_state=False, closed_loop=False, delta_inputs=False):
+    def step_host(self, host_in, host_out, chunks=0, resident_state=False, closed_loop=False, delta_inputs=False, cfg=None):
         """One tick with HOST buffers (what a caller holding NumPy arrays pays end to end): one C-ABI call,
         ``wbc_step_host``.
 
@@ -680,7 +678,9 @@ class RobotModel:
         ~3e-8, times 1 / dt = 500 in the target laws) only guarantee it for the joint position targets.  ``chunks=0``: with page-locked tensors the kernel reads the
         inputs from and writes the outputs to host memory directly (zero-copy, one launch); with pageable tensors, or
         ``chunks >= 1``, the batch is cut into slices that go host -> device, through the fused kernel and back on three
-        streams owned by the model; the current stream waits for all of them.  Returns (h2d_bytes, d2h_bytes).
+        streams owned by the model; the current stream waits for all of them.  ``cfg``: a ``WbcConfig`` built earlier with
+        ``_config()`` (settings that do not change from tick to tick need not be marshalled again).
+        Returns (h2d_bytes, d2h_bytes).
         """
         N, nq, nv = self.N, self.n_configuration_dimensions, self.n_velocity_dimensions
         if closed_loop:
@@ -696,7 +696,10 @@ class RobotModel:
             t = host_in[k]
             if t.device.type != "cpu" or t.dtype != fdt or not t.is_contiguous() or t.shape[0] != N:
                 raise ValueError(f"host_in[{k!r}] must be a contiguous {fdt} CPU tensor with {N} rows")
-        for k in outs + ("status", "iters"):
+        reports = tuple(k for k in ("status", "iters") if host_out.get(k) is not None)
+        if "status" not in reports:
+            raise ValueError("host_out['status'] is required")
+        for k in outs + reports:
             t, dt_ = host_out[k], (fdt if k in outs else torch.int32)
             if t.device.type != "cpu" or t.dtype != dt_ or not t.is_contiguous() or t.shape[0] != N:
                 raise ValueError(f"host_out[{k!r}] must be a contiguous {dt_} CPU tensor with {N} rows")
@@ -735,15 +738,16 @@ class RobotModel:
                 host.ref = host_in["ref"].data_ptr()
             host.qdot = host_out["qdot"].data_ptr()
         host.status = host_out["status"].data_ptr()
-        host.iters = host_out["iters"].data_ptr()
+        if "iters" in reports:
+            host.iters = host_out["iters"].data_ptr()
         with torch.cuda.device(self.device):
-            cabi.check(self._lib.wbc_step_host(self._model, C.byref(self._config()), C.byref(io), C.byref(host), N,
-                                               int(chunks), _stream_ptr()))
+            cabi.check(self._lib.wbc_step_host(self._model, C.byref(cfg if cfg is not None else self._config()), C.byref(io),
+                                               C.byref(host), N, int(chunks), _stream_ptr()))
         if closed_loop:
             self.firstQP = False
         esz = 4 if fdt == torch.float32 else 8
         h2d = sum(host_in[k].numel() * esz for k in moved)
-        d2h = sum(host_out[k].numel() * esz for k in outs) + host_out["status"].numel() * 4 + host_out["iters"].numel() * 4
+        d2h = sum(host_out[k].numel() * esz for k in outs) + sum(host_out[k].numel() * 4 for k in reports)
         return h2d, d2h
 
     def runWBC(self, base_config, target_cartesian_pos_EE=None, target_cartesian_pos_trunk=None):
