@@ -340,8 +340,10 @@ class Ctx:
         return self.torch.cuda.Event(enable_timing=True)
 
 
-def make_robot(ctx, name, n, dt, tasks, cons, joint, seed, sigma, extra=None, lo=0, n_global=None):
-    """RobotModel over this rank's contiguous shard [lo, lo + n) of the global synthetic batch."""
+def make_robot(ctx, name, n, dt, tasks, cons, joint, seed, sigma, extra=None, lo=0, n_global=None, standing=False):
+    """RobotModel over this rank's contiguous shard [lo, lo + n) of the global synthetic batch.  `standing`: the
+    closed-loop sampler (near-level trunk around a standing pose, synthetic.sample_standing) instead of uniformly random
+    configurations."""
     import wbc_b200
     from wbc_b200 import synthetic
     robot = wbc_b200.RobotModel(name, batch=n, device=ctx.dev, dt=dt)
@@ -350,7 +352,7 @@ def make_robot(ctx, name, n, dt, tasks, cons, joint, seed, sigma, extra=None, lo
     if extra:
         robot.extra_rows = extra(robot.robot_model)
     n_global = n_global or n
-    qg = synthetic.sample_configurations(robot.robot_model, n_global, seed)
+    qg = (synthetic.sample_standing if standing else synthetic.sample_configurations)(robot.robot_model, n_global, seed)
     ng = synthetic.sample_noise(n_global, seed, sigma)
     targets = synthetic.load_batch(robot, qg[lo:lo + n], ng[lo:lo + n])
     robot._pack_targets(targets[:, :15].reshape(n, 5, 3), targets[:, 15:18])
@@ -481,8 +483,14 @@ def run_ours(args):
     assert torch.equal(robot._mem, mem0), "the open-loop pass must leave the task memory untouched"
 
     # ---- end to end: the runWBC tick through RobotModel.step_host -> wbc_step_host with HOST buffers ----------
+    # Closed-loop legs run on the closed-loop sampler (standing poses, near-level trunk): the reference's base estimator
+    # (trunkWorldPos, quirk D.10) presupposes it, see synthetic.sample_standing.  Same robot, task stack and constraints.
     nq, nv = table.nq, table.nv
     pin = dict(pin_memory=True)
+    open_robot, open_targets, open_q0, open_mem0, open_ref0 = robot, targets, q0, mem0, ref0
+    robot, targets = make_robot(ctx, args.robot, n_local, args.dt, ALL_TASKS, P2_CONS, True, args.seed + 1, args.sigma, lo=lo,
+                                n_global=n_global, standing=True)
+    mem0, ref0, q0 = robot._mem.clone(), robot._ref.clone(), robot.current_joint_config.clone()
     RING = 8                          # distinct pinned input buffers used round-robin: 8 x 23 MB > L2, and targets do move
     gen = torch.Generator(device="cpu"); gen.manual_seed(args.seed + 17 + rank)
     t_cpu = targets.cpu()
@@ -559,9 +567,13 @@ def run_ours(args):
     out32 = host_out(torch.float32, True)
     f32_value, h2d32, d2h32, f32_solved, _ = e2e_closed(best, ring32, out32, max(5, e2e_steps // 4), delta=True)
 
+    closed_robot = robot
+    robot, targets, q0, mem0, ref0 = open_robot, open_targets, open_q0, open_mem0, open_ref0      # back to the headline batch
+
     def e2e_open(resident, steps):
         reset_state()
-        hin = {"q": q0.cpu().pin_memory(), "targets": t_cpu.pin_memory(), "mem": mem0.cpu().pin_memory(), "ref": ref0.cpu().pin_memory()}
+        hin = {"q": q0.cpu().pin_memory(), "targets": targets.cpu().pin_memory(), "mem": mem0.cpu().pin_memory(),
+               "ref": ref0.cpu().pin_memory()}
         out = host_out(torch.float64, False)
         for _ in range(3):
             h2d_, d2h_ = robot.step_host(hin, out, chunks=0, resident_state=resident)
@@ -579,6 +591,7 @@ def run_ours(args):
     open_all = e2e_open(False, max(5, e2e_steps // 16))
     e2e_ok = e2e_ok and open_res[3] and open_all[3]
     reset_state()
+    del closed_robot
 
     # ---- single-state latency: one robot, one launch (the reference's own use case: a 500 Hz control tick) ----
     lat_us = None
@@ -680,7 +693,8 @@ def run_ours(args):
                            "position targets + status + iterations are written to pinned HOST buffers; configuration, task "
                            "memory and references are the controller's state: resident on the device and ADVANCED IN PLACE "
                            "every step (prev targets / reference rotations, integrate, IMU feedback, base re-estimate), as "
-                           "runWBC mutates its object.  " +
+                           "runWBC mutates its object.  States: standing poses with a near-level trunk (the reference's base "
+                           "estimator presupposes it, quirk D.10); same robot, task stack and constraints as `value`.  " +
                            ("zero-copy: the kernel reads / writes the pinned host buffers over PCIe itself, one launch per step"
                             if best <= 0 else f"{best} staged slices pipelined over 3 streams (cudaMemcpyAsync H2D, kernel, D2H)"),
                     "host_path": "zero_copy" if best <= 0 else f"staged_{best}",
@@ -743,7 +757,8 @@ def rollout_line(ctx, args, robots_per_gpu, K):
     """BASELINE config 5: closed-loop horizon -- K Euler-integrated ticks of `robots_per_gpu` robots per GPU, state resident on
     the device, one fused launch per tick (wbc_rollout)."""
     torch = ctx.torch
-    rr, targets = make_robot(ctx, args.robot, robots_per_gpu, args.dt, ALL_TASKS, P2_CONS, True, args.seed + 50 + 1000 * ctx.rank, args.sigma)
+    rr, targets = make_robot(ctx, args.robot, robots_per_gpu, args.dt, ALL_TASKS, P2_CONS, True, args.seed + 50 + 1000 * ctx.rank, args.sigma,
+                             standing=True)
     if args.rollout_max_iter > 0:
         rr.max_qp_iterations = args.rollout_max_iter
     q0, mem0 = rr.current_joint_config.clone(), rr._mem.clone()
@@ -765,7 +780,8 @@ def rollout_line(ctx, args, robots_per_gpu, K):
         ms = ctx.max_ms(r0.elapsed_time(r1))
         best = ms if best is None else min(best, ms)
     return {"config": "configs[4]", "what": f"closed-loop rollout: {K} Euler-integrated WBC ticks over {n} robots per GPU, task memory and "
-                                            "configuration advanced in place on the device, one fused launch per tick",
+                                            "configuration advanced in place on the device, one fused launch per tick; standing-pose "
+                                            "sampler (near-level trunk: the reference's base estimator presupposes it, quirk D.10)",
             "robot": args.robot, "states_per_gpu": n, "ticks": K, "robots": n * ctx.world,
             "steps_per_s": n * ctx.world * K / (best * 1e-3), "ms_per_tick": best / K,
             "qp_iteration_cap": rr.max_qp_iterations,

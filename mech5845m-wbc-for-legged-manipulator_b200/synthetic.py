@@ -55,6 +55,47 @@ def sample_configurations(table, N, seed, gripper_joint="gripper"):
     return q
 
 
+def sample_standing(table, N, seed, joint_sigma=0.1, tilt=0.03, gripper_joint="gripper"):
+    """[N, nq] configurations around a standing pose with a near-level trunk: the closed-loop workloads.
+
+    The reference's base estimator rotates an already world-frame offset by the trunk rotation once more
+    (``trunkWorldPos``, Robot_Wrapper4.py:1303-1324), so its closed loop only makes sense for a trunk
+    that is close to the identity orientation -- as in its own simulation (``sim3.py``: a standing robot facing +x).
+    With the +-0.3 rad random base attitudes of ``sample_configurations`` every tick displaces the estimated base by
+    centimetres and the arm runs into its velocity limits.  Here: base x, y ~ U(-0.5, 0.5), z = 0.3, attitude
+    from_euler('xyz', U(-tilt, tilt)^3); legs around the standing pattern of ``Robot_Wrapper.py:26-28`` (hip 0, thigh 0.85,
+    calf -1.15), arm joints around 40 % of their range, all + N(0, joint_sigma^2), clipped 5 % inside the limits;
+    gripper = 0, fingers = (+0.02, -0.02)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nq = table.nq
+    q = np.zeros((N, nq))
+    q[:, 0:2] = rng.uniform(-0.5, 0.5, size=(N, 2))
+    q[:, 2] = 0.3
+    q[:, 3:7] = _quat_from_euler_xyz(rng.uniform(-tilt, tilt, size=(N, 3)))
+    lo = np.asarray(table.lower[:nq], dtype=float)
+    up = np.asarray(table.upper[:nq], dtype=float)
+    for j in range(2, table.njoints):
+        iq, name = table.idx_q[j], table.joint_names[j]
+        if name.endswith("_hip_joint"):
+            mean = 0.0
+        elif name.endswith("_thigh_joint"):
+            mean = 0.85
+        elif name.endswith("_calf_joint"):
+            mean = -1.15
+        else:
+            mean = lo[iq] + 0.4 * (up[iq] - lo[iq])
+        margin = 0.05 * (up[iq] - lo[iq])
+        q[:, iq] = np.clip(mean + rng.normal(0.0, joint_sigma, size=N), lo[iq] + margin, up[iq] - margin)
+    g = table.getJointId(gripper_joint)
+    if g < table.njoints:
+        iq = table.idx_q[g]
+        q[:, iq] = 0.0
+        if iq + 2 < nq:
+            q[:, iq + 1] = 0.02
+            q[:, iq + 2] = -0.02
+    return q
+
+
 def sample_noise(N, seed, sigma):
     """[N, 18] target offsets: 5 EE x 3 + trunk 3."""
     rng = np.random.Generator(np.random.PCG64(seed + 7919))
