@@ -576,8 +576,14 @@ static int check_device(const WbcModel* model) {
 
 static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15); }
 
+#ifndef WBC_ONLY_HOT
+#define WBC_ONLY_HOT 0         // 1: A/B builds -- only the bench instantiation (nv = 26, reduced front) is compiled (30 s instead of 3 min)
+#endif
 template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0, bool RED = false>
 static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
+  if constexpr (WBC_ONLY_HOT && !(NV == 26 && !DBG && SPLIT && !FD && NF == 3 && RED)) {
+    return fail(WBC_ERR_UNSUPPORTED, "this is a WBC_ONLY_HOT build: only the nv = 26 reduced-front instantiation exists%s");
+  } else {
   constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
   const size_t per_warp = (size_t)L.total * sizeof(double);
   int max_optin = 0;
@@ -604,6 +610,7 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
   kern<<<grid, warps * 32, smem, st>>>(P);
   CUDA_TRY(cudaGetLastError());
   return WBC_OK;
+  }
 }
 
 template <int NV, bool DBG>
@@ -626,8 +633,24 @@ static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_
   return fd ? launch_step_k<NV, DBG, false, true>(model, P, st, info) : launch_step_k<NV, DBG, false, false>(model, P, st, info);
 }
 
+// TMA staging of the input block: float64 arrays with 16-byte aligned bases.  WBC_B200_BULK=<mask> overrides the policy
+// (bit 0 targets, 1 task memory, 2 references, 3 IMU quaternion; 0 = everything on cp.async): A/B runs.
+static void set_bulk(StepParams* P) {
+  static const int forced = [] { const char* e = getenv("WBC_B200_BULK"); return e && e[0] ? atoi(e) : -1; }();
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  int want = forced >= 0 ? forced : P->bulk_in;
+  if (P->f32_in) want = 0;
+  if (!al(P->io.targets)) want &= ~WBC_BULK_TARGETS;
+  if (!al(P->io.mem_in)) want &= ~WBC_BULK_MEM;
+  if (!al(P->io.ref)) want &= ~WBC_BULK_REF;
+  if (!P->io.imu_quat || !al(P->io.imu_quat)) want &= ~WBC_BULK_IMU;
+  P->bulk_in = want;
+}
+
 template <bool DBG>
-static int launch_step(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
+static int launch_step(const WbcModel* model, const StepParams& P_in, cudaStream_t st, int* info) {
+  StepParams P = P_in;
+  set_bulk(&P);
   switch (model->host.nv) {
     case 25: return launch_step_t<25, DBG>(model, P, st, info);
     case 26: return launch_step_t<26, DBG>(model, P, st, info);
@@ -710,6 +733,10 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   if (P->nC > WBC_MAX_NC) return fail(WBC_ERR_UNSUPPORTED, "more than 32 constraint rows%s");
   P->grid_cap = 0;
   P->f32_in = P->f32_out = 0;
+  // TMA staging policy, by measurement (profiles/r2_ab_bulk_copies.txt): device-resident inputs of a device-resident tick
+  // are 1.8 % faster on plain cp.async, so it is off here; wbc_step_host switches it on for the closed-loop zero-copy tick,
+  // where the per-tick inputs come out of pinned host memory (+4.7 % end to end)
+  P->bulk_in = 0;
   if (io->joint_targets && !io->q_next) return fail(WBC_ERR_INVALID_ARG, "joint_targets needs q_next%s");
   set_reduced(model->host, P);
   return WBC_OK;
@@ -928,6 +955,10 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
     if (mapped) {
       for (int k = 0; k < 9; ++k)
         if (arr[k].h) *arr[k].d = dptr[k];
+      // closed-loop tick from host buffers: targets / IMU quaternion (host) and task memory / references (device) are staged
+      // by the TMA engine (cp.async.bulk + mbarrier); the open-loop call, whose q rows travel by cp.async next to them,
+      // measured 9 % slower with it and keeps cp.async (set_bulk() drops what is not float64 / 16-byte aligned)
+      if (io->q_next) P.bulk_in = WBC_BULK_TARGETS | WBC_BULK_MEM | WBC_BULK_REF | WBC_BULK_IMU;
       P.N = N;
       return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
     }

@@ -20,6 +20,7 @@
 #define WBC_IN_IMU 28       // 4: the IMU quaternion fed back after the tick (runWBC's base_config) -- in the tail of the q
                             //    slot (the fused kernel is instantiated for nq <= 28 only), so that the block stays 148 wide:
                             //    the general instantiation's 12 warps per SM fill the 227 KB of shared memory to the byte
+#define WBC_IN_MBAR 32      // 1: the mbarrier the bulk (TMA) copies of this buffer complete on -- also in the tail of the q slot
 #define WBC_IN_TOTAL 148
 #define WBC_HOT_FRAMES 6
 #define WBC_STEP_FLAG_WEIGHTS_IDENTITY 0x10000   // internal (set by the host wrapper): every 6x6 task weight is I
@@ -84,7 +85,16 @@ struct StepParams {
   // optional FP32 I/O (wbc_step_host with WBC_HOST_F32): which arrays hold float32 elements instead of float64
   int f32_in;                                     // WBC_F32_Q | _TARGETS | _MEM | _REF | _IMU
   int f32_out;                                    // WBC_F32_QDOT | _JOINTS
+  // targets / task memory / references (/ IMU quaternion) are staged by bulk asynchronous copies (cp.async.bulk, the
+  // TMA engine: one instruction per array and state, completion on an mbarrier) instead of one 8-byte cp.async per lane
+  // and 32 doubles: float64 arrays whose base pointers are 16-byte aligned (their rows are 144 / 576 / 192 / 32 B).  Rows
+  // of q (8 nq = 216 B for A1+WX200) are only 8-byte aligned and stay on cp.async.
+  int bulk_in;                                    // WBC_BULK_TARGETS | _MEM | _REF | _IMU (0: everything on cp.async)
 };
+#define WBC_BULK_TARGETS 1
+#define WBC_BULK_MEM 2
+#define WBC_BULK_REF 4
+#define WBC_BULK_IMU 8
 #define WBC_F32_Q 1
 #define WBC_F32_TARGETS 2
 #define WBC_F32_MEM 4
@@ -178,6 +188,33 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const double* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- bulk asynchronous copies (TMA engine, non-tensor form) + mbarrier ------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mb, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mb, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` of transactions on `mb`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mb) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mb)
+               : "memory");
+}
+// all lanes poll; a copy that never completes (a bug, not a data-dependent event) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(mb), "r"(parity)
+                 : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();
+  } while (!done);
+}
+
 __device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -205,7 +242,32 @@ template <int NV>
 __device__ __forceinline__ void prefetch_inputs(const StepParams& P, long long s, uint32_t in_a, int lane) {
   constexpr int nq = NV + 1;
   const WbcStepIO& io = P.io;
-  if (P.f32_in == 0) {                           // (uniform) the float64 layout: straight-line, one instruction per 32 doubles
+  if (P.bulk_in) {                               // (uniform) q by cp.async, the selected 16-byte aligned rows by the TMA engine
+    const int bm = P.bulk_in;
+    const double* qg = io.q + s * nq;
+    if (lane < nq) cp_async8(in_a + 8 * (WBC_IN_Q + lane), qg + lane);
+    const double* tg = io.targets + s * WBC_TARGETS_STRIDE;
+    const double* mg = io.mem_in + s * WBC_MEM_STRIDE;
+    const double* rg = io.ref + s * WBC_REF_STRIDE;
+    const bool imu = io.imu_quat != nullptr;
+    if (lane == 0) {
+      const uint32_t mb = in_a + 8 * WBC_IN_MBAR;
+      mbar_expect_tx(mb, ((bm & WBC_BULK_TARGETS) ? 8u * WBC_TARGETS_STRIDE : 0u) + ((bm & WBC_BULK_MEM) ? 8u * WBC_MEM_STRIDE : 0u) +
+                             ((bm & WBC_BULK_REF) ? 8u * WBC_REF_STRIDE : 0u) + ((imu && (bm & WBC_BULK_IMU)) ? 32u : 0u));
+      if (bm & WBC_BULK_TARGETS) bulk_g2s(in_a + 8 * WBC_IN_TARGETS, tg, 8 * WBC_TARGETS_STRIDE, mb);
+      if (bm & WBC_BULK_MEM) bulk_g2s(in_a + 8 * WBC_IN_MEM, mg, 8 * WBC_MEM_STRIDE, mb);
+      if (bm & WBC_BULK_REF) bulk_g2s(in_a + 8 * WBC_IN_REF, rg, 8 * WBC_REF_STRIDE, mb);
+      if (imu && (bm & WBC_BULK_IMU)) bulk_g2s(in_a + 8 * WBC_IN_IMU, io.imu_quat + s * 4, 32, mb);
+    }
+    if (!(bm & WBC_BULK_TARGETS) && lane < WBC_TARGETS_STRIDE) cp_async8(in_a + 8 * (WBC_IN_TARGETS + lane), tg + lane);
+    if (!(bm & WBC_BULK_MEM)) {
+      cp_async8(in_a + 8 * (WBC_IN_MEM + lane), mg + lane);
+      cp_async8(in_a + 8 * (WBC_IN_MEM + 32 + lane), mg + 32 + lane);
+      if (lane < WBC_MEM_STRIDE - 64) cp_async8(in_a + 8 * (WBC_IN_MEM + 64 + lane), mg + 64 + lane);
+    }
+    if (!(bm & WBC_BULK_REF) && lane < WBC_REF_STRIDE) cp_async8(in_a + 8 * (WBC_IN_REF + lane), rg + lane);
+    if (imu && !(bm & WBC_BULK_IMU) && lane < 4) cp_async8(in_a + 8 * (WBC_IN_IMU + lane), io.imu_quat + s * 4 + lane);
+  } else if (P.f32_in == 0) {                    // (uniform) the float64 layout: straight-line, one instruction per 32 doubles
     const double* qg = io.q + s * nq;
     if (lane < nq) cp_async8(in_a + 8 * (WBC_IN_Q + lane), qg + lane);
     if (nq > 32 && lane == 0) cp_async8(in_a + 8 * (WBC_IN_Q + 32), qg + 32);
@@ -635,6 +697,16 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
 
   const long long stride = (long long)gridDim.x * wpc;
   int buf = 0;
+  uint32_t mb_phase = 0;                        // bit b: parity the next wait on buffer b's mbarrier expects
+  if (P.bulk_in) {
+    if (lane == 0) {
+      mbar_init(in0_a + 8 * WBC_IN_MBAR, 1);
+      mbar_init(in0_a + 8 * (WBC_IN_TOTAL + WBC_IN_MBAR), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+  }
   {
     long long s0 = (long long)blockIdx.x * wpc + warp;
     if (s0 >= P.N) s0 = P.N - 1;
@@ -644,11 +716,15 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     long long sidx = base + warp;
     const bool valid = sidx < P.N;
     if (!valid) sidx = P.N - 1;
-    if (DEBUG_OUT && !valid) break;
     const uint32_t in_a = in0_a + 8 * WBC_IN_TOTAL * buf;
     const uint32_t q_a = in_a + 8 * WBC_IN_Q, tg_a = in_a + 8 * WBC_IN_TARGETS;
     const uint32_t mem_a = in_a + 8 * WBC_IN_MEM, ref_a = in_a + 8 * WBC_IN_REF;
     cp_async_wait_all();
+    if (P.bulk_in) {                                     // (uniform) the bulk copies of this buffer have landed
+      mbar_wait(in_a + 8 * WBC_IN_MBAR, (mb_phase >> buf) & 1u);
+      mb_phase ^= 1u << buf;
+    }
+    if (DEBUG_OUT && !valid) break;                      // (after the waits: no copy may be in flight when the CTA exits)
     if (P.f32_in) widen_inputs<NV>(P, in_a, lane);       // (uniform) optional FP32 I/O
     phase_sync<PS && (WBC_SYNC_TOP != 0)>();
     // the next state's inputs travel while this tick computes: the other buffer is free (its last reader was the tail
@@ -658,6 +734,10 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     if (base + stride < P.N) {
       long long ns = base + stride + warp;
       if (ns >= P.N) ns = P.N - 1;
+      if (P.bulk_in) {           // the previous tick's generic-proxy writes into that buffer (prev targets / rotations) are
+        fence_proxy_async();     // ordered before the TMA engine's writes
+        __syncwarp();
+      }
       prefetch_inputs<NV>(P, ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
     }
 
