@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) wbc_qp_reg_kernel(const __grid_constant__
     QpRegShared S;
     S.R = smem_addr(Hs); S.col = smem_addr(col); S.vd = smem_addr(vd); S.C = smem_addr(Cs);
     S.clb = smem_addr(bnd); S.cub = S.clb + 8 * 32; S.dd = S.clb + 8 * 64;
-    S.red_rows = S.feet_mask = S.red_blk = S.b = 0; S.skip_act = P.active_set == nullptr;
+    S.red_rows = S.feet_mask = S.red_blk = S.red_other = S.b = 0; S.skip_act = P.active_set == nullptr;
     double x;
     const QpResult res = warp_qp_solve_reg<NV, SPLIT>(S, h, hdiag, nC, gk, lbv, ubv, P.max_iter, x);
     if (lane < n) P.x[s * n + lane] = x;
@@ -667,6 +667,7 @@ static void set_reduced(const DevModel& M, StepParams* P) {
   P->red_rows = 0;
   P->red_feet_mask = 0;
   P->red_blk = 0;
+  P->red_other = 0;
   const char* off = getenv("WBC_B200_NO_REDUCED");
   if (off && off[0] == '1') return;
   if (P->nC > 16 || P->row_com >= 0 || P->row_ee[4] >= 0) return;
@@ -689,6 +690,14 @@ static void set_reduced(const DevModel& M, StepParams* P) {
   if (P->row_trunk >= 0 && ((unsigned)M.frame_supp[WBC_FRAME_TRUNK] & legs)) return;
   for (int e = 0; e < P->cfg.n_extra_rows; ++e)
     if ((unsigned)M.frame_supp[P->cfg.extra_frame[e]] & legs) return;
+  {
+    int m = 0;                               // the rows of C that are not foot rows, in order: one per spare lane NV + m
+    for (int r = 0; r < P->nC; ++r)
+      if (!((P->red_feet_mask >> r) & 1u)) {
+        if (m >= 4) return;                  // (nC <= 16 with 12 foot rows: cannot happen)
+        P->red_other |= (unsigned)r << (8 * m++);
+      }
+  }
   P->red_ok = 1;
 }
 
@@ -733,7 +742,7 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   if (P->nC > WBC_MAX_NC) return fail(WBC_ERR_UNSUPPORTED, "more than 32 constraint rows%s");
   P->grid_cap = 0;
   P->f32_in = P->f32_out = 0;
-  // TMA staging policy, by measurement (profiles/r2_ab_bulk_copies.txt): device-resident inputs of a device-resident tick
+  // TMA staging policy, by measurement (profiles/r2_ab_experiments.txt): device-resident inputs of a device-resident tick
   // are 1.8 % faster on plain cp.async, so it is off here; wbc_step_host switches it on for the closed-loop zero-copy tick,
   // where the per-tick inputs come out of pinned host memory (+4.7 % end to end)
   P->bulk_in = 0;

@@ -49,6 +49,7 @@ struct QpRegShared {   // 32-bit shared-window addresses (smem_addr), all 16-byt
   // [6 + 3 j, 9 + 3 j), one byte per j; bit mask of the twelve foot rows
   uint32_t red_rows, feet_mask;
   uint32_t red_blk;  // 2 bits per foot task t: j of its limb columns [6 + 3 j, 9 + 3 j)
+  uint32_t red_other; // one byte per spare lane NV + m: the m-th row of C that is not a foot row (at most four)
   uint32_t b;        // [36] targets of the Cartesian task rows
   uint32_t skip_act; // non-zero: the caller does not want the active-set bit masks (QpResult::act_box / act_rows stay 0)
 };

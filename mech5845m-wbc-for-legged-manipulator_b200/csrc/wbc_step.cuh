@@ -80,7 +80,7 @@ struct StepParams {
   // reduced (null-space) QP front (wbc_qp_red.inc): usable for this model + configuration, first C row of the foot
   // owning limb columns [6 + 3 j, 9 + 3 j) (one byte per j), bit mask of the foot rows; set_reduced()
   int red_ok;
-  unsigned red_rows, red_feet_mask, red_blk;
+  unsigned red_rows, red_feet_mask, red_blk, red_other;
   int grid_cap;                                   // > 0: at most this many CTAs (wbc_step_host runs two slices side by side)
   // optional FP32 I/O (wbc_step_host with WBC_HOST_F32): which arrays hold float32 elements instead of float64
   int f32_in;                                     // WBC_F32_Q | _TARGETS | _MEM | _REF | _IMU
@@ -1145,7 +1145,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       QpRegShared S;
       S.R = hs_a; S.col = ws_a + 8 * L.col; S.vd = vd_a; S.C = ast_a;
       S.clb = clb_a; S.cub = cub_a; S.dd = bs_a;
-      S.red_rows = P.red_rows; S.feet_mask = P.red_feet_mask; S.red_blk = P.red_blk;
+      S.red_rows = P.red_rows; S.feet_mask = P.red_feet_mask; S.red_blk = P.red_blk; S.red_other = P.red_other;
       S.b = bs_a; S.skip_act = P.io.active_set == nullptr;
       res = warp_qp_solve_reg_impl<NV, SPLIT, PS && (WBC_QP_MID_SYNC != 0), NF, RED>(S, h, hdiag, nC, gk, lbv, ubv, cfg.max_iter,
                                                                                     x, a, aj, bj);

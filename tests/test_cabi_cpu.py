@@ -164,3 +164,48 @@ def test_mocap_ingestion_matches_the_fixture_rows(tmp_path):
     assert np.abs(mocap.bullet_to_pinocchio(mocap.pinocchio_to_bullet(rows)) - rows).max() == 0.0
     q = mocap.configurations(frames)
     assert q.shape == (rows.shape[0], 27) and (q[:, 6] == 1.0).all()
+
+
+def test_config_marshalling_bulk_copies_match_the_attributes():
+    """RobotModel._config(): the controller's weights / gains / switches land in the WbcConfig fields the kernel reads
+    (bulk NumPy copies into the ctypes arrays; the gain list is taken as given, quirk D.8)."""
+    from wbc_b200 import _cabi as cabi
+    from wbc_b200.robot_model import RobotModel
+    r = RobotModel.__new__(RobotModel)                       # no device needed: _config only reads attributes
+    rng = np.random.default_rng(0)
+    r.setTasks(Trunk=True, FR=True, FL=False, RR=True, RL=True, Grip=True, Joint="HYBRID")
+    r.setConstraints(CoM=False, Trunk=True, FR=True, FL=True, RR=True, RL=True, Grip=False)
+    r.compat_damper_off_by_one, r.end_effector_index_list_joint, r.arm_base_id, r.max_qp_iterations = True, [7, 4, 13, 10, 19], 14, 77
+    r.EE_weight = [rng.normal(size=(6, 6)) for _ in range(5)]
+    r.EE_gains = [rng.normal(size=(6, 6)) for _ in range(5)]
+    r.trunk_weight, r.trunk_gain = rng.normal(size=(6, 6)), rng.normal(size=(6, 6))
+    r.cart_task_weight_EE_list, r.cart_task_weight_Trunk, r.joint_task_weight = [1, 2, 3, 4, 5], 6, 0.05
+    r.damper, r.extra_rows = (0.01, 0.026, 0.015), [(1, 2, [1, 2, 3, 4, 5, 6], -1.0, 1.0)]
+    c = r._config()
+    for i in range(5):
+        assert np.array_equal(np.array(c.ee_weight[i][:]), r.EE_weight[i].reshape(-1))
+        assert np.array_equal(np.array(c.ee_gain_pos[i][:]), r.EE_gains[i][:3, :3].reshape(-1))
+    assert np.array_equal(np.array(c.trunk_weight[:]), r.trunk_weight.reshape(-1))
+    assert list(c.cart_task_weight[:]) == [1, 2, 3, 4, 5, 6] and c.joint_task_weight == 0.05
+    assert np.array_equal(np.array(c.trunk_gain_pos[:]), r.trunk_gain[:3, :3].reshape(-1))
+    assert np.array_equal(np.array(c.trunk_gain_ori[:]), np.diagonal(r.trunk_gain)[3:])
+    assert c.task_mask == (cabi.TASK_TRUNK | cabi.TASK_FR | cabi.TASK_RR | cabi.TASK_RL | cabi.TASK_GRIP | cabi.TASK_JOINT)
+    assert c.joint_mode == cabi.JOINT_HYBRID and c.max_iter == 77 and c.gripper_joint_id == 19 and c.arm_base_id == 14
+    assert c.n_extra_rows == 1 and list(c.extra_coeff[0][:]) == [1, 2, 3, 4, 5, 6] and (c.extra_lo[0], c.extra_hi[0]) == (-1.0, 1.0)
+
+
+def test_standing_sampler_and_config3_rows():
+    """The closed-loop sampler stays inside the URDF limits with a near-level trunk; config 3's rows are 16 pyramid faces
+    + 7 torque-limit proxy rows built from the URDF's effort / velocity limits."""
+    from wbc_b200 import synthetic, TreeTable
+    for name in ("a1_wx200", "a1_px100_pin_ver", "laikago_vx300"):
+        t = TreeTable.load(name)
+        q = synthetic.sample_standing(t, 512, 3)
+        lo, up = np.asarray(t.lower[7:t.nq]), np.asarray(t.upper[7:t.nq])
+        assert (q[:, 7:] >= lo - 1e-12).all() and (q[:, 7:] <= up + 1e-12).all()
+        assert np.abs(np.linalg.norm(q[:, 3:7], axis=1) - 1).max() < 1e-12 and (q[:, 6] > 0.999).all()
+    t = TreeTable.load("a1_wx200")
+    rows = synthetic.config3_rows(t)
+    assert len(rows) == 23 and all(len(r[2]) == 6 for r in rows)
+    assert [r[0] for r in rows[:16]] == [f for f in range(4) for _ in range(4)] and all(r[4] == 0.0 for r in rows[:16])
+    assert all(r[3] == -r[4] and r[4] > 0 for r in rows[16:])
