@@ -57,8 +57,11 @@ __device__ __forceinline__ void stage_model(const DevModel* __restrict__ g, DevM
 #ifndef WBC_STEP_WARPS_RED
 #define WBC_STEP_WARPS_RED 16 // the reduced-front instantiation: 128 registers, 13.5 KB of shared memory per warp
 #endif
+#ifndef WBC_STEP_WARPS_FULL
+#define WBC_STEP_WARPS_FULL 12 // the full-width solver layout (more than 16 rows of C): 168 registers with ~0.8 KB of spills, yet 14 % faster than 8 warps at 255 (config 3)
+#endif
 template <bool SPLIT, bool RED = false> struct StepWarps {
-  static constexpr int value = RED ? WBC_STEP_WARPS_RED : (SPLIT ? WBC_STEP_WARPS : 8);
+  static constexpr int value = RED ? WBC_STEP_WARPS_RED : (SPLIT ? WBC_STEP_WARPS : WBC_STEP_WARPS_FULL);
   static constexpr int ctas = SPLIT ? WBC_STEP_CTAS : 1;
 };
 
@@ -624,8 +627,10 @@ static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_
     // last three DoFs (both arms) the solver eliminates them at compile time
     if (NV - (P.cfg.gripper_joint_id - 2 + 6) == 3) {
       // the twelve foot equality rows eliminated up front (wbc_qp_red.inc) when model and configuration allow it
+      // (also with the finite-difference joint task, "MANI" / "HYBRID": what sim3.py:145-148 runs)
       if constexpr (!DBG)
-        if (P.red_ok && !fd) return launch_step_k<NV, DBG, true, false, 3, true>(model, P, st, info);
+        if (P.red_ok) return fd ? launch_step_k<NV, DBG, true, true, 3, true>(model, P, st, info)
+                                : launch_step_k<NV, DBG, true, false, 3, true>(model, P, st, info);
       return fd ? launch_step_k<NV, DBG, true, true, 3>(model, P, st, info) : launch_step_k<NV, DBG, true, false, 3>(model, P, st, info);
     }
     return fd ? launch_step_k<NV, DBG, true, true>(model, P, st, info) : launch_step_k<NV, DBG, true, false>(model, P, st, info);
