@@ -567,6 +567,36 @@ def run_ours(args):
     out32 = host_out(torch.float32, True)
     f32_value, h2d32, d2h32, f32_solved, _ = e2e_closed(best, ring32, out32, max(5, e2e_steps // 4), delta=True)
 
+    # the box's ceiling for this traffic pattern: plain cudaMemcpyAsync of the tick's host buffers, both directions at once, all
+    # ranks at once (no kernel) -- what the host side of PCIe / host memory gives each GPU when `world` GPUs pull together
+    def pcie_ceiling(reps=20):
+        src_h = torch.cat([ring64[0]["targets"].reshape(-1), ring64[0]["imu"].reshape(-1)]).pin_memory()
+        dst_d = torch.empty_like(src_h, device=dev)
+        src_d = torch.empty(out64["joint_targets"].numel() + n_local // 2 + 1, dtype=torch.float64, device=dev)
+        dst_h = torch.empty(src_d.shape, dtype=torch.float64, **pin)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        def burst(n):
+            for _ in range(n):
+                with torch.cuda.stream(s_in):
+                    dst_d.copy_(src_h, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    dst_h.copy_(src_d, non_blocking=True)
+        burst(3)
+        torch.cuda.synchronize()
+        ctx.barrier()
+        a, b = ctx.event(), ctx.event()
+        a.record()
+        s_in.wait_stream(torch.cuda.current_stream()); s_out.wait_stream(torch.cuda.current_stream())
+        burst(reps)
+        torch.cuda.current_stream().wait_stream(s_in); torch.cuda.current_stream().wait_stream(s_out)
+        b.record()
+        ctx.barrier()
+        ms = ctx.max_ms(a.elapsed_time(b))
+        return {"h2d": src_h.numel() * 8 * reps / ms / 1e6, "d2h": src_d.numel() * 8 * reps / ms / 1e6,
+                "what": "cudaMemcpyAsync of one tick's pinned host buffers, both directions concurrently, every rank at the same "
+                        "time, no kernel: the ceiling the box gives the end-to-end leg at this GPU count"}
+    pcie_peak = pcie_ceiling()
+
     closed_robot = robot
     robot, targets, q0, mem0, ref0 = open_robot, open_targets, open_q0, open_mem0, open_ref0      # back to the headline batch
 
@@ -701,6 +731,8 @@ def run_ours(args):
                     "host_path_candidates_steps_per_s": {("zero_copy" if k <= 0 else f"staged_{k}"): v for k, v in variants.items()},
                     "gpu_launches_per_step": 1 if best <= 0 else best,
                     "pcie_gbs_per_gpu": {"h2d": pcie(e2e_value, h2d), "d2h": pcie(e2e_value, d2h)},
+                    "pcie_memcpy_ceiling_gbs_per_gpu": pcie_peak,
+                    "frac_of_pcie_ceiling": max(pcie(e2e_value, h2d) / pcie_peak["h2d"], pcie(e2e_value, d2h) / pcie_peak["d2h"]),
                     "equals_device_rollout": e2e_ok,
                     "fp32_io": {"value": f32_value, "unit": UNIT, "dtype": "f32 host I/O (increment inputs), f64 arithmetic",
                                 "h2d_bytes_per_step": h2d32, "d2h_bytes_per_step": d2h32, "solved_fraction_last_tick": f32_solved,
