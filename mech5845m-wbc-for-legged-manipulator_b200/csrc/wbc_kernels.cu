@@ -70,7 +70,7 @@ template <bool SPLIT, bool RED = false> struct StepWarps {
 #else
 #define WBC_STEP_BOUNDS(SPLIT, RED) __launch_bounds__(32 * StepWarps<SPLIT, RED>::value, StepWarps<SPLIT, RED>::ctas)
 #endif
-template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF, bool RED>
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF, bool RED, bool MULTI>
 __global__ void WBC_STEP_BOUNDS(SPLIT, RED) wbc_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
@@ -78,7 +78,7 @@ __global__ void WBC_STEP_BOUNDS(SPLIT, RED) wbc_step_kernel(const __grid_constan
   constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
   const int warp = threadIdx.x >> 5;
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
-  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF, RED>(P, Ms, ws);
+  warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF, RED, MULTI>(P, Ms, ws);
 }
 
 // FK + frame Jacobians accessor (HBM-write bound): one state per warp
@@ -582,7 +582,7 @@ static size_t model_smem_bytes() { return (sizeof(DevModel) + 15) & ~size_t(15);
 #ifndef WBC_ONLY_HOT
 #define WBC_ONLY_HOT 0         // 1: A/B builds -- only the bench instantiation (nv = 26, reduced front) is compiled (30 s instead of 3 min)
 #endif
-template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0, bool RED = false>
+template <int NV, bool DBG, bool SPLIT, bool FD, int NF = 0, bool RED = false, bool MULTI = false>
 static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_t st, int* info) {
   if constexpr (WBC_ONLY_HOT && !(NV == 26 && !DBG && SPLIT && !FD && NF == 3 && RED)) {
     return fail(WBC_ERR_UNSUPPORTED, "this is a WBC_ONLY_HOT build: only the nv = 26 reduced-front instantiation exists%s");
@@ -596,7 +596,7 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
   if (warps > StepWarps<SPLIT, RED>::value) warps = StepWarps<SPLIT, RED>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
   const size_t smem = model_smem_bytes() + warps * per_warp;
-  auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD, NF, RED>;
+  auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD, NF, RED, MULTI>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + warps - 1) / warps;
   long long cap = (long long)model->sm_count * ctas;
@@ -628,9 +628,12 @@ static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_
     if (NV - (P.cfg.gripper_joint_id - 2 + 6) == 3) {
       // the twelve foot equality rows eliminated up front (wbc_qp_red.inc) when model and configuration allow it
       // (also with the finite-difference joint task, "MANI" / "HYBRID": what sim3.py:145-148 runs)
-      if constexpr (!DBG)
+      if constexpr (!DBG) {
+        // the whole closed-loop horizon in one launch (wbc_rollout; the usual joint-task modes only)
+        if (P.red_ok && !fd && P.K > 1) return launch_step_k<NV, DBG, true, false, 3, true, true>(model, P, st, info);
         if (P.red_ok) return fd ? launch_step_k<NV, DBG, true, true, 3, true>(model, P, st, info)
                                 : launch_step_k<NV, DBG, true, false, 3, true>(model, P, st, info);
+      }
       return fd ? launch_step_k<NV, DBG, true, true, 3>(model, P, st, info) : launch_step_k<NV, DBG, true, false, 3>(model, P, st, info);
     }
     return fd ? launch_step_k<NV, DBG, true, true>(model, P, st, info) : launch_step_k<NV, DBG, true, false>(model, P, st, info);
@@ -751,6 +754,7 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   // are 1.8 % faster on plain cp.async, so it is off here; wbc_step_host switches it on for the closed-loop zero-copy tick,
   // where the per-tick inputs come out of pinned host memory (+4.7 % end to end)
   P->bulk_in = 0;
+  P->K = 1;
   if (io->joint_targets && !io->q_next) return fail(WBC_ERR_INVALID_ARG, "joint_targets needs q_next%s");
   set_reduced(model->host, P);
   return WBC_OK;
@@ -1065,13 +1069,26 @@ int wbc_rollout(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io
   tick.q_next = const_cast<double*>(io->q);
   tick.mem_out = const_cast<double*>(io->mem_in);
   StepParams P;
+  if (N < 0 || !tick.qdot || !tick.status || !tick.iters) return fail(WBC_ERR_INVALID_ARG, "qdot / status / iters are required%s");
+  if (K == 0 || N == 0) return WBC_OK;
+  tick.targets = targets_traj;
+  tick.imu_quat = imu_traj;
+  int rc = check_cfg(model, cfg, &tick, &P);
+  if (rc != WBC_OK) return rc;
+  P.N = N;
+  // The whole horizon in ONE launch where the reduced-front instantiation applies (four foot constraints, <= 16 rows, the
+  // usual joint-task modes): a robot stays with one warp for all K ticks, so nothing separates the ticks but that warp's own
+  // program order -- no relaunch, no drain tail per tick.  WBC_B200_ROLLOUT_LAUNCHES=1 forces one launch per tick (A/B runs).
+  static const bool per_tick = [] { const char* e = getenv("WBC_B200_ROLLOUT_LAUNCHES"); return e && e[0] == '1'; }();
+  const bool fd = (P.cfg.task_mask & WBC_TASK_JOINT) && (P.cfg.joint_mode == WBC_JOINT_MANI || P.cfg.joint_mode == WBC_JOINT_HYBRID);
+  const bool locked3 = model->host.nv - (P.cfg.gripper_joint_id - 2 + 6) == 3;
+  if (K > 1 && !per_tick && P.red_ok && P.nC <= 16 && locked3 && !fd && (model->host.nv == 25 || model->host.nv == 26)) {
+    P.K = K;
+    return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
+  }
   for (int k = 0; k < K; ++k) {
-    tick.targets = targets_traj + (size_t)k * N * WBC_TARGETS_STRIDE;
-    tick.imu_quat = imu_traj ? imu_traj + (size_t)k * N * 4 : nullptr;
-    int rc = check_cfg(model, cfg, &tick, &P);
-    if (rc != WBC_OK) return rc;
-    if (N < 0 || !tick.qdot || !tick.status || !tick.iters) return fail(WBC_ERR_INVALID_ARG, "qdot / status / iters are required%s");
-    P.N = N;
+    P.io.targets = targets_traj + (size_t)k * N * WBC_TARGETS_STRIDE;
+    P.io.imu_quat = imu_traj ? imu_traj + (size_t)k * N * 4 : nullptr;
     rc = launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
     if (rc != WBC_OK) return rc;
   }

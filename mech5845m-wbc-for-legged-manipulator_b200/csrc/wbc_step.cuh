@@ -90,6 +90,9 @@ struct StepParams {
   // and 32 doubles: float64 arrays whose base pointers are 16-byte aligned (their rows are 144 / 576 / 192 / 32 B).  Rows
   // of q (8 nq = 216 B for A1+WX200) are only 8-byte aligned and stay on cp.async.
   int bulk_in;                                    // WBC_BULK_TARGETS | _MEM | _REF | _IMU (0: everything on cp.async)
+  // closed-loop horizon in ONE launch (the MULTI instantiation, wbc_rollout): K ticks; io.targets / io.imu_quat are then
+  // trajectories [K, N, 18] / [K, N, 4], q and the task memory are advanced in place (io.q_next == io.q, io.mem_out == io.mem_in)
+  int K;
 };
 #define WBC_BULK_TARGETS 1
 #define WBC_BULK_MEM 2
@@ -238,15 +241,16 @@ __device__ __forceinline__ void prefetch_slot(uint32_t slot_a, const double* src
 
 // fetch the input block of state s: q, targets, task memory, references (+ the IMU quaternion): 1128 (+ 32) B for
 // nq = 27, coalesced
+// (sv: row of the state in io.targets / io.imu_quat -- s itself, or k N + s for tick k of a multi-tick launch)
 template <int NV>
-__device__ __forceinline__ void prefetch_inputs(const StepParams& P, long long s, uint32_t in_a, int lane) {
+__device__ __forceinline__ void prefetch_inputs(const StepParams& P, long long s, long long sv, uint32_t in_a, int lane) {
   constexpr int nq = NV + 1;
   const WbcStepIO& io = P.io;
   if (P.bulk_in) {                               // (uniform) q by cp.async, the selected 16-byte aligned rows by the TMA engine
     const int bm = P.bulk_in;
     const double* qg = io.q + s * nq;
     if (lane < nq) cp_async8(in_a + 8 * (WBC_IN_Q + lane), qg + lane);
-    const double* tg = io.targets + s * WBC_TARGETS_STRIDE;
+    const double* tg = io.targets + sv * WBC_TARGETS_STRIDE;
     const double* mg = io.mem_in + s * WBC_MEM_STRIDE;
     const double* rg = io.ref + s * WBC_REF_STRIDE;
     const bool imu = io.imu_quat != nullptr;
@@ -257,7 +261,7 @@ __device__ __forceinline__ void prefetch_inputs(const StepParams& P, long long s
       if (bm & WBC_BULK_TARGETS) bulk_g2s(in_a + 8 * WBC_IN_TARGETS, tg, 8 * WBC_TARGETS_STRIDE, mb);
       if (bm & WBC_BULK_MEM) bulk_g2s(in_a + 8 * WBC_IN_MEM, mg, 8 * WBC_MEM_STRIDE, mb);
       if (bm & WBC_BULK_REF) bulk_g2s(in_a + 8 * WBC_IN_REF, rg, 8 * WBC_REF_STRIDE, mb);
-      if (imu && (bm & WBC_BULK_IMU)) bulk_g2s(in_a + 8 * WBC_IN_IMU, io.imu_quat + s * 4, 32, mb);
+      if (imu && (bm & WBC_BULK_IMU)) bulk_g2s(in_a + 8 * WBC_IN_IMU, io.imu_quat + sv * 4, 32, mb);
     }
     if (!(bm & WBC_BULK_TARGETS) && lane < WBC_TARGETS_STRIDE) cp_async8(in_a + 8 * (WBC_IN_TARGETS + lane), tg + lane);
     if (!(bm & WBC_BULK_MEM)) {
@@ -266,12 +270,12 @@ __device__ __forceinline__ void prefetch_inputs(const StepParams& P, long long s
       if (lane < WBC_MEM_STRIDE - 64) cp_async8(in_a + 8 * (WBC_IN_MEM + 64 + lane), mg + 64 + lane);
     }
     if (!(bm & WBC_BULK_REF) && lane < WBC_REF_STRIDE) cp_async8(in_a + 8 * (WBC_IN_REF + lane), rg + lane);
-    if (imu && !(bm & WBC_BULK_IMU) && lane < 4) cp_async8(in_a + 8 * (WBC_IN_IMU + lane), io.imu_quat + s * 4 + lane);
+    if (imu && !(bm & WBC_BULK_IMU) && lane < 4) cp_async8(in_a + 8 * (WBC_IN_IMU + lane), io.imu_quat + sv * 4 + lane);
   } else if (P.f32_in == 0) {                    // (uniform) the float64 layout: straight-line, one instruction per 32 doubles
     const double* qg = io.q + s * nq;
     if (lane < nq) cp_async8(in_a + 8 * (WBC_IN_Q + lane), qg + lane);
     if (nq > 32 && lane == 0) cp_async8(in_a + 8 * (WBC_IN_Q + 32), qg + 32);
-    const double* tg = io.targets + s * WBC_TARGETS_STRIDE;
+    const double* tg = io.targets + sv * WBC_TARGETS_STRIDE;
     if (lane < WBC_TARGETS_STRIDE) cp_async8(in_a + 8 * (WBC_IN_TARGETS + lane), tg + lane);
     const double* mg = io.mem_in + s * WBC_MEM_STRIDE;
     cp_async8(in_a + 8 * (WBC_IN_MEM + lane), mg + lane);
@@ -279,13 +283,13 @@ __device__ __forceinline__ void prefetch_inputs(const StepParams& P, long long s
     if (lane < WBC_MEM_STRIDE - 64) cp_async8(in_a + 8 * (WBC_IN_MEM + 64 + lane), mg + 64 + lane);
     const double* rg = io.ref + s * WBC_REF_STRIDE;
     if (lane < WBC_REF_STRIDE) cp_async8(in_a + 8 * (WBC_IN_REF + lane), rg + lane);
-    if (io.imu_quat && lane < 4) cp_async8(in_a + 8 * (WBC_IN_IMU + lane), io.imu_quat + s * 4 + lane);
+    if (io.imu_quat && lane < 4) cp_async8(in_a + 8 * (WBC_IN_IMU + lane), io.imu_quat + sv * 4 + lane);
   } else {
     prefetch_slot(in_a + 8 * WBC_IN_Q, io.q, s, nq, P.f32_in & WBC_F32_Q, lane);
-    prefetch_slot(in_a + 8 * WBC_IN_TARGETS, io.targets, s, WBC_TARGETS_STRIDE, P.f32_in & WBC_F32_TARGETS, lane);
+    prefetch_slot(in_a + 8 * WBC_IN_TARGETS, io.targets, sv, WBC_TARGETS_STRIDE, P.f32_in & WBC_F32_TARGETS, lane);
     prefetch_slot(in_a + 8 * WBC_IN_MEM, io.mem_in, s, WBC_MEM_STRIDE, P.f32_in & WBC_F32_MEM, lane);
     prefetch_slot(in_a + 8 * WBC_IN_REF, io.ref, s, WBC_REF_STRIDE, P.f32_in & WBC_F32_REF, lane);
-    if (io.imu_quat) prefetch_slot(in_a + 8 * WBC_IN_IMU, io.imu_quat, s, 4, P.f32_in & WBC_F32_IMU, lane);
+    if (io.imu_quat) prefetch_slot(in_a + 8 * WBC_IN_IMU, io.imu_quat, sv, 4, P.f32_in & WBC_F32_IMU, lane);
   }
   cp_async_commit();
 }
@@ -663,7 +667,10 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 // one fetch feeds all warps.  Padding warps shadow the last state (no writes) so the barriers stay uniform.
 // Shared memory is addressed through 32-bit shared-window addresses (wbc_device.cuh: smem_addr, lds_*, sts_*).
 // NF: the last NF velocity DoFs are locked by the configuration (gripper + fingers, lb = ub = 0): the QP runs on NV - NF variables
-template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0, bool RED = false>
+// MULTI: P.K consecutive closed-loop ticks in this one launch.  A robot belongs to one warp for the whole horizon (its q and
+// task memory are advanced in place by that warp alone), so no grid-wide synchronisation separates the ticks: a CTA walks
+// (tick 0: its rounds), (tick 1: its rounds), ... and only the last tick of the horizon has a drain tail.
+template <int NV, bool DEBUG_OUT, bool SPLIT, bool FD, int NF = 0, bool RED = false, bool MULTI = false>
 __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevModel* Ms, double* ws) {
   constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
   static_assert(NV + 1 <= WBC_IN_IMU, "the IMU quaternion sits behind q inside the q slot");
@@ -696,6 +703,11 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
   const bool w_ident = (P.flags & WBC_STEP_FLAG_WEIGHTS_IDENTITY) != 0;        // every 6x6 task weight is the identity
 
   const long long stride = (long long)gridDim.x * wpc;
+  const long long first = (long long)blockIdx.x * wpc;
+  // MULTI: the next tick of a robot reads what this tick's tail wrote.  With two or more rounds per tick the prefetch at the
+  // top of an iteration fetches a state whose previous tick ended at least one iteration ago; with a single round it is the
+  // state in flight, so the prefetch moves behind the tail (`late`)
+  const bool late = MULTI && first + stride >= P.N;
   int buf = 0;
   uint32_t mb_phase = 0;                        // bit b: parity the next wait on buffer b's mbarrier expects
   if (P.bulk_in) {
@@ -708,11 +720,15 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     __syncwarp();
   }
   {
-    long long s0 = (long long)blockIdx.x * wpc + warp;
+    long long s0 = first + warp;
     if (s0 >= P.N) s0 = P.N - 1;
-    prefetch_inputs<NV>(P, s0, in0_a, lane);
+    prefetch_inputs<NV>(P, s0, s0, in0_a, lane);
   }
-  for (long long base = (long long)blockIdx.x * wpc; base < P.N; base += stride) {
+  // (toff = k N: row offset of tick k in the target / IMU trajectories; 0 and dead code unless MULTI)
+  long long toff = 0;
+  int tick = 0;
+  for (long long base = first; MULTI ? (tick < P.K && first < P.N) : (base < P.N);
+       base += stride, (MULTI && base >= P.N) ? (base = first, toff += P.N, ++tick) : 0) {
     long long sidx = base + warp;
     const bool valid = sidx < P.N;
     if (!valid) sidx = P.N - 1;
@@ -731,15 +747,24 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     // of the previous tick), and a whole tick -- ~20 us per warp -- hides the latency even of a PCIe read (zero-copy
     // host buffers).  Issued here, not in front of the QP, so that its address arithmetic does not sit in the kernel's
     // region of highest register pressure.
-    if (base + stride < P.N) {
-      long long ns = base + stride + warp;
-      if (ns >= P.N) ns = P.N - 1;
-      if (P.bulk_in) {           // the previous tick's generic-proxy writes into that buffer (prev targets / rotations) are
-        fence_proxy_async();     // ordered before the TMA engine's writes
-        __syncwarp();
+    auto prefetch_next = [&]() {
+      bool more = base + stride < P.N;                   // another state in this tick ...
+      long long ns = base + stride + warp, nv_off = MULTI ? toff : 0;
+      if (MULTI && !more && tick + 1 < P.K) {            // ... or the first one of the next tick
+        more = true;
+        ns = first + warp;
+        nv_off = toff + P.N;
       }
-      prefetch_inputs<NV>(P, ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
-    }
+      if (ns >= P.N) ns = P.N - 1;
+      if (more) {
+        if (P.bulk_in) {         // the previous tick's generic-proxy writes into that buffer (prev targets / rotations) are
+          fence_proxy_async();   // ordered before the TMA engine's writes
+          __syncwarp();
+        }
+        prefetch_inputs<NV>(P, ns, nv_off + ns, in0_a + 8 * WBC_IN_TOTAL * (buf ^ 1), lane);
+      }
+    };
+    if (!late) prefetch_next();
 
     // ---------------------------------------------------------------- kinematics
     double Sc[6];                        // column `lane` of data.J (WORLD): [lin; ang]
@@ -1238,6 +1263,10 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
         else P.io.joint_targets[sidx * (nq - 7) + lane] = jt;
       }
       __syncwarp();
+    }
+    if (MULTI && late) {               // single round per tick: the state just written is the next one to read
+      __syncwarp();
+      prefetch_next();
     }
     buf ^= 1;
   }

@@ -765,23 +765,25 @@ class RobotModel:
         grip = joint_config[:, 12:]
         return FL_leg, FR_leg, RL_leg, RR_leg, grip
 
-    def rollout(self, target_EE_traj, target_trunk_traj, imu_quat_traj=None, record=False):
-        """Closed-loop horizon (BASELINE config 5): K consecutive runWBC ticks (:1330-1412) for all N robots, one fused
-        launch per tick; task memory and configuration stay resident on the device between ticks.
+    def rollout(self, target_EE_traj, target_trunk_traj, imu_quat_traj=None, record=False, report_active_set=True):
+        """Closed-loop horizon (BASELINE config 5): K consecutive runWBC ticks (:1330-1412) for all N robots; task memory and
+        configuration stay resident on the device between ticks.  One persistent launch for the whole horizon where the
+        reduced-front kernel applies (wbc_rollout), else one fused launch per tick.
 
         ``target_EE_traj`` [K, N, 5, 3], ``target_trunk_traj`` [K, N, 3], optional ``imu_quat_traj`` [K, N, 4] (base
         orientation fed back each tick; default: the integrated orientation).  Returns qdot of the last tick, or with
         ``record`` the tuple (q history [K, N, nq], qdot history [K, N, nv], status history [K, N]).
+        ``report_active_set=False``: the active-set bit masks of the last tick are not packed (as in ``step``).
         """
         K = int(target_EE_traj.shape[0])
         if not record:
-            # one C-ABI call: K launches back to back, q and task memory advanced in place on the device
+            # one C-ABI call: q and task memory advanced in place on the device
             traj = torch.cat((target_EE_traj.to(self.device, torch.float64).reshape(K, self.N, 15),
                               target_trunk_traj.to(self.device, torch.float64).reshape(K, self.N, 3)), dim=2).contiguous()
             imu = imu_quat_traj.to(self.device, torch.float64).reshape(K, self.N, 4).contiguous() if imu_quat_traj is not None else None
             self.current_joint_config = self.current_joint_config.contiguous().clone()
             io = self._io(targets=traj, qdot=self.qdot, status=self.last_status, iters=self.last_iters,
-                          active_set=self.last_active_set)
+                          active_set=self.last_active_set if report_active_set else None)
             with torch.cuda.device(self.device):
                 cabi.check(self._lib.wbc_rollout(self._model, C.byref(self._config()), C.byref(io), _ptr(traj), _ptr(imu), K,
                                                  self.N, _stream_ptr()))

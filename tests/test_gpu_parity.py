@@ -262,6 +262,64 @@ def test_closed_loop_rollout_matches_oracle():
     assert worst_v < QP_TOL and worst_q < 1e-8, (worst_v, worst_q)
 
 
+@pytest.mark.parametrize("name", ["a1_wx200", "a1_px100_pin_ver"])
+def test_closed_loop_reach_trajectory_matches_oracle(name):
+    """A horizon of the length and shape the reference's driver runs (sim3.py:287-327: a standing robot, feet planted, the
+    gripper reaching along a trajectory while the trunk sways): 120 closed-loop ticks with the IMU quaternion fed back, on
+    the standing-pose sampler.  Every tick of every robot is compared with the oracle loop: solution, configuration, status,
+    iteration count and active set -- so bounds and trunk-box rows that become active and inactive along the way do so at
+    the same tick on both sides.  The horizon runs as one persistent launch (wbc_rollout) and tick by tick."""
+    from wbc_b200 import synthetic
+    N, K = 6, 120
+    robot = _robot(name, N, P1_TASKS, P2_CONS, True)
+    q = synthetic.sample_standing(robot.robot_model, N, 20260061)
+    targets = synthetic.load_batch(robot, q, np.zeros((N, 18)))
+    mem0, ref0 = robot._mem.clone().cpu().numpy(), robot._ref.clone().cpu().numpy()
+    t = torch.arange(1, K + 1, dtype=torch.float64, device="cuda:0")[:, None] * robot.dt
+    amp = torch.as_tensor(np.random.default_rng(7).uniform(0.5, 1.0, size=(N,)), device="cuda:0")[None, :]
+    traj = targets[None].repeat(K, 1, 1)
+    traj[:, :, 12] += 0.10 * amp * torch.sin(2 * np.pi * 2.0 * t)           # gripper x: 10 cm reach, 2 Hz
+    traj[:, :, 14] += 0.06 * amp * (1 - torch.cos(2 * np.pi * 2.0 * t))     # gripper z
+    traj[:, :, 16] += 0.02 * amp * torch.sin(2 * np.pi * 1.0 * t)           # trunk sway y
+    traj[:, :, 17] -= 0.03 * amp * (1 - torch.cos(2 * np.pi * 1.0 * t))     # trunk z: crouch towards the trunk box
+    imu = torch.as_tensor(q[:, 3:7], device="cuda:0")[None].repeat(K, 1, 1)
+    ee, tr = traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18]
+    qh, vh, sh = robot.rollout(ee, tr, imu_quat_traj=imu, record=True)
+    twin = _robot(name, N, P1_TASKS, P2_CONS, True)
+    twin.current_joint_config = torch.as_tensor(q, device="cuda:0").clone()
+    twin._mem.copy_(torch.as_tensor(mem0, device="cuda:0")); twin._ref.copy_(torch.as_tensor(ref0, device="cuda:0"))
+    twin.rollout(ee, tr, imu_quat_traj=imu)
+    assert torch.equal(twin.current_joint_config, qh[-1]) and torch.equal(twin._mem, robot._mem)
+    assert (sh == 0).all()
+    # per-tick iteration counts / active sets of the device loop (record=True steps tick by tick)
+    robot.current_joint_config = torch.as_tensor(q, device="cuda:0").clone()
+    robot._mem.copy_(torch.as_tensor(mem0, device="cuda:0"))
+    its, acts = [], []
+    for k in range(K):
+        robot.step(ee[k], tr[k], imu_quat=imu[k], advance=True)
+        its.append(robot.last_iters.cpu().numpy().copy()); acts.append(robot.last_active_set.cpu().numpy().astype(np.uint64).copy())
+    assert torch.equal(robot.current_joint_config, qh[-1])
+    qh, vh = qh.cpu().numpy(), vh.cpu().numpy()
+    rm = H.make_oracle(name, like=robot, dt=robot.dt)
+    traj_h, imu_h = traj.cpu().numpy(), imu.cpu().numpy()
+    worst_q = worst_v = 0.0
+    n_ineq = 0
+    for s in range(N):
+        qs, mem = q[s].copy(), mem0[s].copy()
+        for k in range(K):
+            r = H.oracle_step_one(rm, qs, traj_h[k, s], mem, ref0[s], imu=imu_h[k, s], solve=True, tail=True)
+            assert r["status"] == 0, (s, k)
+            worst_v = max(worst_v, np.abs(vh[k, s] - r["qdot"]).max())
+            worst_q = max(worst_q, np.abs(qh[k, s] - r["q_next"]).max())
+            wb, wr = H.act_to_bits(r["act"], robot.n_velocity_dimensions)
+            assert r["iters"] == int(its[k][s]) and wb == int(acts[k][s, 0]) and wr == int(acts[k][s, 1]), (s, k)
+            n_ineq += r["iters"] - 15
+            qs, mem = r["q_next"], H.get_oracle_mem(rm)
+    print(name, "reach trajectory: worst |dv|", worst_v, "worst |dq|", worst_q, "inequality iterations", n_ineq)
+    assert worst_v < QP_TOL and worst_q < 1e-8, (worst_v, worst_q)
+    assert n_ineq > 0                  # the horizon does drive constraints active
+
+
 def test_config3_extension_rows_full_size():
     """BASELINE config 3: A1 + WX200, 65,536 states, friction-pyramid + torque-limit proxy rows through the generic
     extension-row channel (NOT in the reference, whose QP is purely kinematic: parity unpinned by construction; both

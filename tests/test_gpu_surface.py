@@ -487,6 +487,34 @@ def test_step_host_closed_loop_equals_rollout(chunks):
     assert torch.equal(robot._mem, mem_end)
 
 
+@pytest.mark.parametrize("name,N,K", [("a1_wx200", 1, 4), ("a1_wx200", 37, 6), ("a1_wx200", 2368, 3), ("a1_wx200", 2369, 3),
+                                      ("a1_px100_pin_ver", 5000, 4), ("a1_wx200", 6000, 1)])
+def test_rollout_in_one_launch_equals_tick_by_tick(name, N, K):
+    """`wbc_rollout` runs the whole closed-loop horizon as ONE persistent launch when the reduced-front instantiation applies
+    (a robot stays with one warp for all K ticks).  It must land bit for bit where K separate fused launches land
+    (`rollout(record=True)` steps tick by tick): batches smaller than one round (every prefetch of the next tick has to wait
+    for the tail: the `late` path), exactly one round of 148 x 16 warps, one state more, several rounds with a ragged last
+    one, and K = 1."""
+    robot = _robot(name, N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260059, 5e-4)
+    q0, mem0, ref0 = robot.current_joint_config.clone(), robot._mem.clone(), robot._ref.clone()
+    gen = torch.Generator(device=DEV); gen.manual_seed(5)
+    traj = targets[None] + torch.randn(K, N, 18, dtype=torch.float64, device=DEV, generator=gen).mul_(2e-4).cumsum(0)
+    imu = q0[:, 3:7][None].repeat(K, 1, 1) + 1e-3 * torch.randn(K, N, 4, dtype=torch.float64, device=DEV, generator=gen)
+    imu = imu / imu.norm(dim=2, keepdim=True)
+    ee, tr = traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18]
+    for with_imu in (True, False):
+        robot.current_joint_config = q0.clone(); robot._mem.copy_(mem0); robot._ref.copy_(ref0)
+        qh, vh, sh = robot.rollout(ee, tr, imu_quat_traj=imu if with_imu else None, record=True)
+        mem_end, it_end, act_end = robot._mem.clone(), robot.last_iters.clone(), robot.last_active_set.clone()
+        robot.current_joint_config = q0.clone(); robot._mem.copy_(mem0); robot._ref.copy_(ref0)
+        v = robot.rollout(ee, tr, imu_quat_traj=imu if with_imu else None)
+        assert torch.equal(robot.current_joint_config, qh[-1]) and torch.equal(v, vh[-1])
+        assert torch.equal(robot.last_status, sh[-1]) and torch.equal(robot._mem, mem_end)
+        assert torch.equal(robot.last_iters, it_end) and torch.equal(robot.last_active_set, act_end)
+        assert torch.equal(robot._ref, ref0)
+
+
 def test_fp32_host_io_mode_agrees_with_fp64():
     """The optional FP32 I/O mode (north_star: "an optional FP32 mode must agree within 1e-4"): float32 arrays on the
     host side, float64 arithmetic in the tick.  Closed loop over several ticks against the float64 call on the same data:
