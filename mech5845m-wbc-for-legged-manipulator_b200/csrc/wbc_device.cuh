@@ -97,6 +97,19 @@ __device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
 
+// six predicated 128-bit stores at a, a + 16, ..., a + 80 behind one compare (lanes with c == false take no part in the
+// store at all: fewer shared-memory wavefronts than dumping their values somewhere)
+__device__ __forceinline__ void sts_f64x12_if(bool c, uint32_t a, const double* v) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %13, 0;\n\t"
+      "@p st.shared.v2.f64 [%0], {%1, %2};\n\t@p st.shared.v2.f64 [%0+16], {%3, %4};\n\t"
+      "@p st.shared.v2.f64 [%0+32], {%5, %6};\n\t@p st.shared.v2.f64 [%0+48], {%7, %8};\n\t"
+      "@p st.shared.v2.f64 [%0+64], {%9, %10};\n\t@p st.shared.v2.f64 [%0+80], {%11, %12};\n\t}"
+      ::"r"(a), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]), "d"(v[8]), "d"(v[9]),
+        "d"(v[10]), "d"(v[11]), "r"((int)c)
+      : "memory");
+}
+
 // Phase barrier: the warps of a group re-align (named barrier per group of WBC_SYNC_GROUP warps; 0 = whole CTA).
 #ifndef WBC_SYNC_GROUP
 #define WBC_SYNC_GROUP -1      // -1: two groups of half the CTA's warps each: 3.4 % faster than one group (less waiting for the slowest QP); three groups thrash the I-cache (-21 %)

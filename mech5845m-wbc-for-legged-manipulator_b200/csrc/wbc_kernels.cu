@@ -76,7 +76,7 @@ __global__ void WBC_STEP_BOUNDS(SPLIT, RED) wbc_step_kernel(const __grid_constan
   DevModel* Ms = reinterpret_cast<DevModel*>(smem_raw);
   stage_model(P.model, Ms);
   constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
-  const int warp = threadIdx.x >> 5;
+  const int warp = SPLIT ? (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5) : (int)(threadIdx.x >> 5);   // warp-uniform for ptxas (see warp_wbc_states)
   double* ws = reinterpret_cast<double*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15))) + (size_t)warp * L.total;
   warp_wbc_states<NV, DEBUG_OUT, SPLIT, FD, NF, RED, MULTI>(P, Ms, ws);
 }
@@ -658,6 +658,7 @@ static void set_bulk(StepParams* P) {
 template <bool DBG>
 static int launch_step(const WbcModel* model, const StepParams& P_in, cudaStream_t st, int* info) {
   StepParams P = P_in;
+  if (P.N >= (1LL << 31) - (1LL << 20)) return fail(WBC_ERR_UNSUPPORTED, "more than 2^31 - 2^20 states per call (the kernel indexes states with 32 bits)%s");
   set_bulk(&P);
   switch (model->host.nv) {
     case 25: return launch_step_t<25, DBG>(model, P, st, info);

@@ -415,32 +415,34 @@ __device__ __forceinline__ void warp_fk_a(uint32_t M_a, uint32_t q_a, uint32_t o
   // memory.  (The association order of the products differs from Pinocchio's root-to-leaf sweep: rounding-level, 1e-16.)
   // Divergence-free: slot 0 (the universe) and the slots of the idle lanes hold the identity, and a joint without a
   // 2^r-th ancestor composes with slot 0 (1 * x + 0 * y + 0 * z is exact), so all 32 lanes run the same code.
+  // Slot index = joint index = lane, so the ancestor's transform comes by warp shuffle straight out of its lane's registers:
+  // no stores between the rounds, no barrier pairs, half the shared-memory pipe time (the pipe is the busiest unit of the
+  // tick, ncu); only the final transforms go to shared memory for the Jacobian columns and the frames.
   const uint32_t out_a = oMi_a + 8 * WBC_T_STRIDE * lane;
   if (!active) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) Rl[i] = (i % 4 == 0) ? 1.0 : 0.0;
     pl[0] = pl[1] = pl[2] = 0.0;
   }
+  const int nrounds = lds_s32(M_a + WBC_MOFF(nrounds));
+#pragma unroll 1
+  for (int r = 0; r < nrounds; ++r) {
+    const int anc = lds_s32(M_a + WBC_MOFF(anc) + 4 * (WBC_MAX_JOINTS * r + lane));
+    double Rp[9], pp[3], R[9], p[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rp[i] = __shfl_sync(WBC_FULL_MASK, Rl[i], anc);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pp[i] = __shfl_sync(WBC_FULL_MASK, pl[i], anc);
+    mat3_mul(Rp, Rl, R);
+    mat3_vec(Rp, pl, p);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rl[i] = R[i];
+    pl[0] = p[0] + pp[0]; pl[1] = p[1] + pp[1]; pl[2] = p[2] + pp[2];
+  }
 #pragma unroll
   for (int i = 0; i < 9; ++i) sts_f64(out_a + 8 * i, Rl[i]);
   sts_f64(out_a + 72, pl[0]); sts_f64(out_a + 80, pl[1]); sts_f64(out_a + 88, pl[2]);
   __syncwarp();
-  const int nrounds = lds_s32(M_a + WBC_MOFF(nrounds));
-#pragma unroll 1
-  for (int r = 0; r < nrounds; ++r) {
-    const uint32_t pa = oMi_a + 8 * WBC_T_STRIDE * lds_s32(M_a + WBC_MOFF(anc) + 4 * (WBC_MAX_JOINTS * r + lane));
-    double Rp[9], pp[3], R[9], p[3];
-    lds_mat3(pa, Rp);
-    lds_vec3(pa + 72, pp);
-    __syncwarp();                      // every ancestor has been read before anyone overwrites its slot
-    mat3_mul(Rp, Rl, R);
-    mat3_vec(Rp, pl, p);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { Rl[i] = R[i]; sts_f64(out_a + 8 * i, R[i]); }
-    pl[0] = p[0] + pp[0]; pl[1] = p[1] + pp[1]; pl[2] = p[2] + pp[2];
-    sts_f64(out_a + 72, pl[0]); sts_f64(out_a + 80, pl[1]); sts_f64(out_a + 88, pl[2]);
-    __syncwarp();
-  }
 }
 #endif
 
@@ -678,7 +680,10 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
   constexpr int LD = NV | 1;
   constexpr int nq = NV + 1;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  // (through a warp reduction: its result is warp-uniform for ptxas, so everything derived from it -- the per-warp shared base,
+  //  the state index, the input buffer -- can live in uniform registers instead of the 128 per-thread ones)
+  //  (measured: 4 096-state, bootstrap, HYBRID and closed-loop launches +4-5 %, headline +0.7 %; the full-width layout -6 %: plain there)
+  const int warp = SPLIT ? (int)__reduce_max_sync(WBC_FULL_MASK, threadIdx.x >> 5) : (int)(threadIdx.x >> 5), wpc = blockDim.x >> 5;
   const WbcConfig& cfg = P.cfg;
   const double dt = P.io.dt;
   const double inv_dt = 1.0 / dt;       // the reference divides by dt; multiplying by 1/dt differs by <= 1 ulp
@@ -702,12 +707,14 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
   const double aj = joint_on ? (1.0 / NV) * cfg.joint_task_weight : 0.0;       // qpJointA (:1199-1206)
   const bool w_ident = (P.flags & WBC_STEP_FLAG_WEIGHTS_IDENTITY) != 0;        // every 6x6 task weight is the identity
 
-  const long long stride = (long long)gridDim.x * wpc;
-  const long long first = (long long)blockIdx.x * wpc;
+  // (32-bit state indices: the host refuses N >= 2^31 - 2^20; 64-bit arithmetic only where an address is formed)
+  const int NS = (int)P.N;
+  const int stride = (int)gridDim.x * wpc;
+  const int first = (int)blockIdx.x * wpc;
   // MULTI: the next tick of a robot reads what this tick's tail wrote.  With two or more rounds per tick the prefetch at the
   // top of an iteration fetches a state whose previous tick ended at least one iteration ago; with a single round it is the
   // state in flight, so the prefetch moves behind the tail (`late`)
-  const bool late = MULTI && first + stride >= P.N;
+  const bool late = MULTI && first + stride >= NS;
   int buf = 0;
   uint32_t mb_phase = 0;                        // bit b: parity the next wait on buffer b's mbarrier expects
   if (P.bulk_in) {
@@ -720,18 +727,19 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     __syncwarp();
   }
   {
-    long long s0 = first + warp;
-    if (s0 >= P.N) s0 = P.N - 1;
+    int s0 = first + warp;
+    if (s0 >= NS) s0 = NS - 1;
     prefetch_inputs<NV>(P, s0, s0, in0_a, lane);
   }
   // (toff = k N: row offset of tick k in the target / IMU trajectories; 0 and dead code unless MULTI)
   long long toff = 0;
   int tick = 0;
-  for (long long base = first; MULTI ? (tick < P.K && first < P.N) : (base < P.N);
-       base += stride, (MULTI && base >= P.N) ? (base = first, toff += P.N, ++tick) : 0) {
-    long long sidx = base + warp;
-    const bool valid = sidx < P.N;
-    if (!valid) sidx = P.N - 1;
+  for (int base = first; MULTI ? (tick < P.K && first < NS) : (base < NS);
+       base += stride, (MULTI && base >= NS) ? (base = first, toff += NS, ++tick) : 0) {
+    int sidx32 = base + warp;
+    const bool valid = sidx32 < NS;
+    if (!valid) sidx32 = NS - 1;
+    const long long sidx = sidx32;
     const uint32_t in_a = in0_a + 8 * WBC_IN_TOTAL * buf;
     const uint32_t q_a = in_a + 8 * WBC_IN_Q, tg_a = in_a + 8 * WBC_IN_TARGETS;
     const uint32_t mem_a = in_a + 8 * WBC_IN_MEM, ref_a = in_a + 8 * WBC_IN_REF;
@@ -748,14 +756,15 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     // host buffers).  Issued here, not in front of the QP, so that its address arithmetic does not sit in the kernel's
     // region of highest register pressure.
     auto prefetch_next = [&]() {
-      bool more = base + stride < P.N;                   // another state in this tick ...
-      long long ns = base + stride + warp, nv_off = MULTI ? toff : 0;
+      bool more = base + stride < NS;                    // another state in this tick ...
+      int ns = base + stride + warp;
+      long long nv_off = MULTI ? toff : 0;
       if (MULTI && !more && tick + 1 < P.K) {            // ... or the first one of the next tick
         more = true;
         ns = first + warp;
-        nv_off = toff + P.N;
+        nv_off = toff + NS;
       }
-      if (ns >= P.N) ns = P.N - 1;
+      if (ns >= NS) ns = NS - 1;
       if (more) {
         if (P.bulk_in) {         // the previous tick's generic-proxy writes into that buffer (prev targets / rotations) are
           fence_proxy_async();   // ordered before the TMA engine's writes
