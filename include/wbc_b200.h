@@ -281,14 +281,23 @@ typedef struct WbcHostIO {
  *                configuration and the task memory are advanced in place exactly as runWBC mutates its object
  *                (:995-996, :1151-1152, :1397-1402); per tick only the IMU quaternion and the targets travel in and the
  *                joint targets / status out.  K calls equal wbc_rollout over the same K ticks.
- *   chunks <= 0  automatic: if every host array is page-locked the kernel reads the inputs from and writes the outputs
- *                to host memory directly (zero-copy, one launch on `stream`); otherwise as chunks = 8;
+ *   chunks < 0   if every host array is page-locked the kernel reads the inputs from and writes the outputs to host memory
+ *                directly (zero-copy, one launch on `stream`); otherwise as chunks = 8;
+ *   chunks == 0  self-tuning: as chunks < 0, but with page-locked arrays and N >= 4096 the model handle measures both host
+ *                paths on the first four calls of a problem shape (two zero-copy launches, two calls with 8 staged slices;
+ *                the second of each is timed with events on `stream`) and runs the faster one from then on -- one GPU
+ *                alone is faster zero-copy, eight GPUs pulling on one host NUMA node are faster staged.  Results do not
+ *                depend on the path.  wbc_step_host_path() reports the decision;
  *   chunks >= 1  staged: the batch is cut into `chunks` wave-aligned slices whose host->device copies, kernel and
  *                device->host copies overlap on three streams owned by the model (created on first use).
  * io->active_set must be NULL.  Asynchronous: `stream` is ordered before the first access and after the last;
  * synchronise it before reading the host outputs.  Not re-entrant per model handle. */
 int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const WbcHostIO* host, int64_t N,
                   int32_t chunks, void* stream);
+
+/* the host path wbc_step_host's self-tuning mode (chunks == 0) settled on for the last problem shape: -1 undecided (fewer
+ * than five calls, or the mode has not been used), 0 zero-copy, 8 staged slices; -2: null handle */
+int wbc_step_host_path(const WbcModel* model);
 
 /* Closed loop: K consecutive ticks (the tick loop of sim3.py:287-327 around runWBC, Robot_Wrapper4.py:1330-1412) for
  * N robots, configuration and task memory advanced in place on the device.  With the usual constraint set (trunk box + four

@@ -36,7 +36,7 @@ EXPORTS = [
     "wbc_abi_version", "wbc_last_error", "wbc_model_create", "wbc_model_destroy", "wbc_config_rows",
     "wbc_fk_jac", "wbc_joint_jacobians", "wbc_init_memory", "wbc_integrate", "wbc_base_estimate", "wbc_assemble",
     "wbc_qp_solve", "wbc_step",
-    "wbc_rollout", "wbc_step_host",
+    "wbc_rollout", "wbc_step_host", "wbc_step_host_path",
     "wbc_step_launch_info", "wbc_measure_fp64_peak",
 ]
 
@@ -140,6 +140,7 @@ def load():
     lib.wbc_qp_solve.argtypes = [i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.wbc_step.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), i64, vp]
     lib.wbc_step_host.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), C.POINTER(WbcHostIO), i64, i32, vp]
+    lib.wbc_step_host_path.argtypes = [vp]
     lib.wbc_rollout.argtypes = [vp, C.POINTER(WbcConfig), C.POINTER(WbcStepIO), vp, vp, i32, i64, vp]
     lib.wbc_step_launch_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.wbc_measure_fp64_peak.argtypes = [C.POINTER(f64), vp]

@@ -32,7 +32,18 @@ struct WbcModel {
   bool pipe_ready;
   cudaStream_t pipe[WBC_PIPE_STREAMS];
   cudaEvent_t pipe_start, pipe_done[WBC_PIPE_STREAMS];
+  // wbc_step_host, chunks == 0: which host path is faster HERE is measured, not assumed (one GPU alone: zero-copy; eight GPUs
+  // pulling on one host NUMA node: staged slices).  Calls 0-1 of a new problem shape run zero-copy, calls 2-3 staged; calls 1
+  // and 3 are timed with events on the caller's stream; from then on the faster one runs.
+  struct HostTune {
+    int64_t N; int key;          // problem shape the measurement belongs to (states; dtype / form / flags)
+    int calls;                   // calls seen with this shape
+    int choice;                  // -1 undecided, 0 zero-copy, 8 staged slices
+    bool ev_ready;
+    cudaEvent_t ev[4];           // [zero-copy begin, end, staged begin, end]
+  } tune;
 };
+#define WBC_HOST_AUTO_STAGED 8
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -771,6 +782,7 @@ int wbc_model_create(const WbcTreeTable* table, WbcModel** out_model) {
   WbcModel* m = new (std::nothrow) WbcModel;
   if (!m) return fail(WBC_ERR_INVALID_ARG, "out of host memory%s");
   m->pipe_ready = false;
+  m->tune.N = -1; m->tune.key = 0; m->tune.calls = 0; m->tune.choice = -1; m->tune.ev_ready = false;
   int rc = build_dev_model(table, &m->host);
   if (rc != WBC_OK) { delete m; return rc; }
   cudaError_t e = cudaGetDevice(&m->device);
@@ -787,6 +799,8 @@ int wbc_model_create(const WbcTreeTable* table, WbcModel** out_model) {
 
 void wbc_model_destroy(WbcModel* model) {
   if (!model) return;
+  if (model->tune.ev_ready)
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(model->tune.ev[k]);
   if (model->pipe_ready) {
     for (int s = 0; s < WBC_PIPE_STREAMS; ++s) {
       cudaStreamSynchronize(model->pipe[s]);
@@ -956,6 +970,7 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
       return fail(WBC_ERR_INVALID_ARG, "increment inputs need float32 host arrays and the closed-loop tick (resident q / task memory)%s");
     P.f32_in |= WBC_F32_DELTA;
   }
+  cudaEvent_t tune_end = nullptr;          // set: record it on the caller's stream when this call has been queued
   if (chunks <= 0) {
     // Zero-copy: when every host array is page-locked (and therefore mapped into the device's address space under
     // unified addressing) the kernel reads the inputs straight from host memory -- its cp.async prefetch runs a whole tick
@@ -971,7 +986,33 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
       if (a.type != cudaMemoryTypeHost || !a.devicePointer) mapped = false;
       else dptr[k] = a.devicePointer;
     }
-    if (mapped) {
+    bool zero_copy = mapped;
+    // chunks == 0: self-tuning between the zero-copy launch and WBC_HOST_AUTO_STAGED staged slices (chunks < 0: zero-copy
+    // whenever the arrays are page-locked).  The staged candidate needs its staging twins.
+    const bool can_stage = !(host->imu_quat && !io->imu_quat) && !(host->joint_targets && !io->joint_targets);
+    if (mapped && chunks == 0 && can_stage && N >= 4096) {
+      WbcModel::HostTune& T = model->tune;
+      const int key = (f32 ? 1 : 0) | (io->q_next ? 2 : 0) | (host->flags << 2) | (host->q ? 64 : 0) | (host->mem_in ? 128 : 0);
+      if (T.N != N || T.key != key) { T.N = N; T.key = key; T.calls = 0; T.choice = -1; }
+      if (!T.ev_ready) {
+        for (int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreate(&T.ev[k]));
+        T.ev_ready = true;
+      }
+      if (T.choice < 0 && T.calls >= 4 && cudaEventQuery(T.ev[1]) == cudaSuccess && cudaEventQuery(T.ev[3]) == cudaSuccess) {
+        float tz = 0.f, ts = 0.f;
+        if (cudaEventElapsedTime(&tz, T.ev[0], T.ev[1]) == cudaSuccess && cudaEventElapsedTime(&ts, T.ev[2], T.ev[3]) == cudaSuccess)
+          T.choice = (ts < 0.97f * tz) ? WBC_HOST_AUTO_STAGED : 0;     // one launch wins a tie
+        else cudaGetLastError();
+      }
+      const int call = T.calls++;
+      if (T.choice >= 0) zero_copy = T.choice == 0;
+      else if (call == 2 || call == 3) zero_copy = false;               // the staged candidate's turn
+      if (T.choice < 0 && (call == 1 || call == 3)) {                   // the second call of each candidate is the timed one
+        CUDA_TRY(cudaEventRecord(T.ev[call == 1 ? 0 : 2], (cudaStream_t)stream));
+        tune_end = T.ev[call == 1 ? 1 : 3];
+      }
+    }
+    if (zero_copy) {
       for (int k = 0; k < 9; ++k)
         if (arr[k].h) *arr[k].d = dptr[k];
       // closed-loop tick from host buffers: targets / IMU quaternion (host) and task memory / references (device) are staged
@@ -979,9 +1020,11 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
       // measured 9 % slower with it and keeps cp.async (set_bulk() drops what is not float64 / 16-byte aligned)
       if (io->q_next) P.bulk_in = WBC_BULK_TARGETS | WBC_BULK_MEM | WBC_BULK_REF | WBC_BULK_IMU;
       P.N = N;
-      return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
+      rc = launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
+      if (rc == WBC_OK && tune_end) CUDA_TRY(cudaEventRecord(tune_end, (cudaStream_t)stream));
+      return rc;
     }
-    chunks = 8;                            // pageable host memory: staged copies
+    chunks = WBC_HOST_AUTO_STAGED;         // pageable host memory, or the staged candidate of the self-tuning mode
   }
   // staged: the device twins of the travelling arrays are the staging space
   if (host->imu_quat && !io->imu_quat) return fail(WBC_ERR_INVALID_ARG, "staged copies: io->imu_quat is needed as staging space%s");
@@ -1058,7 +1101,13 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
   }
   if (rc != WBC_OK) return rc;
   if (ce != cudaSuccess) return fail(WBC_ERR_CUDA, "wbc_step_host: %s", cudaGetErrorString(ce));
+  if (tune_end) CUDA_TRY(cudaEventRecord(tune_end, user));
   return WBC_OK;
+}
+
+int wbc_step_host_path(const WbcModel* model) {
+  if (!model) return -2;
+  return model->tune.choice;
 }
 
 int wbc_rollout(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, const double* targets_traj,

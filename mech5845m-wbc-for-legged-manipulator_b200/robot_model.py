@@ -675,10 +675,12 @@ class RobotModel:
         inside).  ``delta_inputs`` (float32, closed loop): ``targets`` / ``imu`` hold INCREMENTS over the previous tick's
         targets / the resident base quaternion (``HostDeltaEncoder`` produces them): a float32 increment is exact to
         ~1e-10, so the mode agrees with the float64 call to < 1e-4 in qdot, where absolute float32 positions (error
-        ~3e-8, times 1 / dt = 500 in the target laws) only guarantee it for the joint position targets.  ``chunks=0``: with page-locked tensors the kernel reads the
+        ~3e-8, times 1 / dt = 500 in the target laws) only guarantee it for the joint position targets.  ``chunks=-1``: with page-locked tensors the kernel reads the
         inputs from and writes the outputs to host memory directly (zero-copy, one launch); with pageable tensors, or
         ``chunks >= 1``, the batch is cut into slices that go host -> device, through the fused kernel and back on three
-        streams owned by the model; the current stream waits for all of them.  ``cfg``: a ``WbcConfig`` built earlier with
+        streams owned by the model; the current stream waits for all of them.  ``chunks=0`` (default): self-tuning -- the
+        first four calls of a problem shape try both (zero-copy twice, 8 slices twice), the faster one runs from then on
+        (``host_path()`` tells which); the results do not depend on the path.  ``cfg``: a ``WbcConfig`` built earlier with
         ``_config()`` (settings that do not change from tick to tick need not be marshalled again).
         Returns (h2d_bytes, d2h_bytes).
         """
@@ -749,6 +751,11 @@ class RobotModel:
         h2d = sum(host_in[k].numel() * esz for k in moved)
         d2h = sum(host_out[k].numel() * esz for k in outs) + sum(host_out[k].numel() * 4 for k in reports)
         return h2d, d2h
+
+    def host_path(self):
+        """What the self-tuning ``step_host(chunks=0)`` settled on: "undecided", "zero_copy" or "staged_8"."""
+        c = int(self._lib.wbc_step_host_path(self._model))
+        return {0: "zero_copy", -1: "undecided"}.get(c, f"staged_{c}")
 
     def runWBC(self, base_config, target_cartesian_pos_EE=None, target_cartesian_pos_trunk=None):
         """Robot_Wrapper4.py:1330-1412, batched.  Like the reference, the QP's report is not acted upon: a state whose QP

@@ -487,6 +487,34 @@ def test_step_host_closed_loop_equals_rollout(chunks):
     assert torch.equal(robot._mem, mem_end)
 
 
+def test_step_host_self_tuning_path_does_not_change_results():
+    """`chunks=0` lets the model handle measure the zero-copy launch against 8 staged slices on its first four calls and keep
+    the faster one (one GPU alone: zero-copy; eight GPUs on one host NUMA node: staged).  Whatever it picks and while it is
+    still trying both, every tick lands where the device rollout lands; afterwards `host_path()` names the decision."""
+    name, N, K = "a1_wx200", 8192, 8
+    robot = _robot(name, N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260067, 5e-4)
+    q0, mem0 = robot.current_joint_config.clone(), robot._mem.clone()
+    gen = torch.Generator(device=DEV); gen.manual_seed(11)
+    traj = targets[None] + torch.randn(K, N, 18, dtype=torch.float64, device=DEV, generator=gen).mul_(2e-4).cumsum(0)
+    imu = q0[:, 3:7][None].repeat(K, 1, 1)
+    qh, vh, sh = robot.rollout(traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18], imu_quat_traj=imu, record=True)
+    robot.current_joint_config = q0.clone(); robot._mem.copy_(mem0)
+    nq = robot.n_configuration_dimensions
+    out = {"joint_targets": torch.empty(N, nq - 7, dtype=torch.float64).pin_memory(), "status": torch.empty(N, dtype=torch.int32).pin_memory()}
+    assert robot.host_path() == "undecided"
+    for k in range(K):
+        host_in = {"targets": traj[k].cpu().pin_memory(), "imu": imu[k].cpu().pin_memory()}
+        robot.step_host(host_in, out, chunks=0, closed_loop=True)
+        torch.cuda.synchronize()
+        assert torch.equal(robot.current_joint_config, qh[k]) and torch.equal(out["joint_targets"], qh[k][:, 7:].cpu()), k
+        assert torch.equal(out["status"], sh[k].cpu())
+    assert robot.host_path() in ("zero_copy", "staged_8")
+    # a forced path leaves the decision alone
+    robot.step_host(host_in, out, chunks=-1, closed_loop=True)
+    assert robot.host_path() in ("zero_copy", "staged_8")
+
+
 @pytest.mark.parametrize("name,N,K", [("a1_wx200", 1, 4), ("a1_wx200", 37, 6), ("a1_wx200", 2368, 3), ("a1_wx200", 2369, 3),
                                       ("a1_px100_pin_ver", 5000, 4), ("a1_wx200", 6000, 1)])
 def test_rollout_in_one_launch_equals_tick_by_tick(name, N, K):
