@@ -117,7 +117,14 @@ __device__ __forceinline__ void sts_f64x12_if(bool c, uint32_t a, const double* 
 template <bool ON>
 __device__ __forceinline__ void phase_sync() {
   if (ON) {
-#if WBC_SYNC_GROUP < 0
+#if WBC_SYNC_GROUP < 0 && defined(WBC_SYNC_SMSP)
+    // A/B: groups by scheduler -- warps 0,1,4,5,... (sub-partitions 0 and 1) against 2,3,6,7,... (sub-partitions 2 and 3), so that
+    // each sub-partition's instruction cache sees one instruction stream
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int g = (wid >> 1) & 1;
+    const int n1 = ((nw >> 2) << 1) + ((nw & 3) > 2 ? (nw & 3) - 2 : 0), n0 = nw - n1;
+    asm volatile("bar.sync %0, %1;" ::"r"(g ? 2 : 1), "r"((g ? n1 : n0) * 32) : "memory");
+#elif WBC_SYNC_GROUP < 0
     const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int half = (nw + 1) >> 1;
     const bool g = wid >= half;
