@@ -209,6 +209,45 @@ def test_full_size_properties_config2():
         assert np.abs(Nm @ lam - gn[s]).max() < 1e-7, s
 
 
+def test_full_size_sweep_config4_one_million_states():
+    """BASELINE configs[3]: the A1 + WX200 sweep over 2^20 states (the bench shards it over eight GPUs; here all of it on one).
+    Size-independent properties: every QP solved; the answer of a state does not depend on the launch it rode in (slices
+    relaunched as batches of their own -- other grid, other rounds, other barrier groups -- give the same bits); a stride
+    sample satisfies its bounds and rows and has J_foot qdot = 0; a stride sample equals the C oracle with the same pivoting
+    path and active set; a checksum of checksums over eight shards equals the checksum of the whole."""
+    from oracle import c_port
+    N = 1 << 20
+    robot = _robot("a1_wx200", N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260003, 5e-4)
+    mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=False).clone()
+    st, it, act = robot.last_status.clone(), robot.last_iters.clone(), robot.last_active_set.clone()
+    assert (st == 0).all() and torch.isfinite(x).all()
+    assert abs(float(sum(x[k * (N // 8):(k + 1) * (N // 8)].abs().sum() for k in range(8))) - float(x.abs().sum())) < 1e-6
+    for lo, n in ((0, 4096), (123457, 2369), (N - 777, 777)):
+        sub = _robot("a1_wx200", n, P1_TASKS, P2_CONS, True)
+        sub.current_joint_config = robot.current_joint_config[lo:lo + n].clone()
+        sub._mem.copy_(mem0[lo:lo + n]); sub._ref.copy_(ref0[lo:lo + n])
+        t = targets[lo:lo + n]
+        xs = sub.step(t[:, :15].reshape(n, 5, 3), t[:, 15:18], advance=False)
+        assert torch.equal(xs, x[lo:lo + n]) and torch.equal(sub.last_iters, it[lo:lo + n])
+        assert torch.equal(sub.last_active_set, act[lo:lo + n])
+        if lo == 0:
+            asm = sub.assemble(t[:, :15].reshape(n, 5, 3), t[:, 15:18], want=("C", "Clb", "Cub", "lb", "ub"))
+            Cx = torch.einsum("nrk,nk->nr", asm["C"], xs)
+            assert (Cx >= asm["Clb"] - 1e-8).all() and (Cx <= asm["Cub"] + 1e-8).all()
+            assert (xs >= asm["lb"] - 1e-9).all() and (xs <= asm["ub"] + 1e-9).all()
+            assert Cx[:, 4:].abs().max() < 1e-8
+    idx = torch.arange(0, N, 257, device="cuda:0")
+    ts, table = c_port.table_struct("a1_wx200")
+    ref = c_port.step(ts, c_port.config_struct(robot, table), q[idx.cpu().numpy()], targets[idx].cpu().numpy(),
+                      mem0[idx].cpu().numpy(), ref0[idx].cpu().numpy(), robot.dt)
+    assert (ref["status"] == 0).all()
+    assert np.abs(x[idx].cpu().numpy() - ref["qdot"]).max() < QP_TOL
+    assert (it[idx].cpu().numpy() == ref["iters"]).all()
+    assert (act[idx].cpu().numpy().astype(np.uint64) == ref["active_set"]).all()
+
+
 def test_config2_every_state_against_the_c_oracle():
     """BASELINE config 2: A1 + PX100, 4096 random states, every solution compared with the CPU loop
     (oracle/wbc_oracle.c, itself pinned against the NumPy/SciPy oracle on the CPU)."""
