@@ -86,6 +86,9 @@ __device__ __forceinline__ int lds_s32(uint32_t a) {
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void lds_vec3(uint32_t a, double* v) {
   v[0] = lds_f64(a); v[1] = lds_f64(a + 8); v[2] = lds_f64(a + 16);
 }

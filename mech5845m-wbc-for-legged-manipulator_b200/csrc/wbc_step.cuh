@@ -1167,6 +1167,15 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     }
 
     // ---------------------------------------------------------------- the QP
+    // The loop state (state index, input buffer, mbarrier phases, tick) is parked in two spare shared-memory words across
+    // the QP and re-derived behind it: carried in registers it is spilled to local memory there anyway (the QP is the
+    // kernel's region of highest register pressure), and local loads miss the 28 KB of L1 half of the time.
+    const uint32_t stash_a = in0_a + 8 * 33, stash_b = in0_a + 8 * (WBC_IN_TOTAL + 33);
+    if (lane == 0) {
+      sts_s32(stash_a, base);
+      sts_s32(stash_a + 4, buf | (int)(mb_phase << 1));
+      if (MULTI) sts_s32(stash_b, tick);
+    }
     double x;
     QpResult res;
     {
@@ -1186,6 +1195,20 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     }
 
     phase_sync<PS && (WBC_SYNC_POSTQP != 0)>();
+    {
+      const int bm = lds_s32(stash_a + 4);
+      base = lds_s32(stash_a);
+      buf = bm & 1;
+      mb_phase = (uint32_t)bm >> 1;
+      if (MULTI) { tick = lds_s32(stash_b); toff = (long long)tick * NS; }
+    }
+    {   // (scope of the re-derived loop state: it shadows what the first half of the tick used)
+    int sidx_p = base + warp;
+    const bool valid = sidx_p < NS;
+    if (!valid) sidx_p = NS - 1;
+    const long long sidx = sidx_p;
+    const uint32_t in_a = in0_a + 8 * WBC_IN_TOTAL * buf;
+    const uint32_t q_a = in_a + 8 * WBC_IN_Q, tg_a = in_a + 8 * WBC_IN_TARGETS, mem_a = in_a + 8 * WBC_IN_MEM;
     if (valid && lane < NV) {
       if (P.f32_out & WBC_F32_QDOT) reinterpret_cast<float*>(P.io.qdot)[sidx * NV + lane] = (float)x;
       else P.io.qdot[sidx * NV + lane] = x;
@@ -1273,6 +1296,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       }
       __syncwarp();
     }
+    }   // re-derived loop state
     if (MULTI && late) {               // single round per tick: the state just written is the next one to read
       __syncwarp();
       prefetch_next();
