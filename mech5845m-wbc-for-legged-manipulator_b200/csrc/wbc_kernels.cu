@@ -767,7 +767,6 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   // where the per-tick inputs come out of pinned host memory (+4.7 % end to end)
   P->bulk_in = 0;
   P->K = 1;
-  for (int t = 0; t < WBC_HOT_FRAMES; ++t) P->frame_supp[t] = model->host.frame_supp[t];
   if (io->joint_targets && !io->q_next) return fail(WBC_ERR_INVALID_ARG, "joint_targets needs q_next%s");
   set_reduced(model->host, P);
   return WBC_OK;

@@ -93,7 +93,6 @@ struct StepParams {
   // closed-loop horizon in ONE launch (the MULTI instantiation, wbc_rollout): K ticks; io.targets / io.imu_quat are then
   // trajectories [K, N, 18] / [K, N, 4], q and the task memory are advanced in place (io.q_next == io.q, io.mem_out == io.mem_in)
   int K;
-  unsigned frame_supp[WBC_HOT_FRAMES];            // DevModel::frame_supp of the six hot frames (launch constants)
 };
 #define WBC_BULK_TARGETS 1
 #define WBC_BULK_MEM 2
@@ -784,9 +783,9 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
 
     // ---------------------------------------------------------------- task rows for my column (registers)
     // EE tasks: A = W (J_LWA w) (:476-482); trunk task: A = (W J_WORLD) w (:488-490)
-    // (support masks of the six hot frames: launch constants, read from the parameter bank where they are needed instead of
-    //  six registers loaded from the tree table and kept across half of the tick)
-    const unsigned* supp = P.frame_supp;
+    uint32_t supp[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) supp[t] = (uint32_t)lds_s32(M_a + WBC_MOFF(frame_supp) + 4 * t);
     double a[36];
     // (computed here only in the finite-difference modes, whose perturbed state must not reach A; otherwise after the
     //  targets and bounds, right before its consumers: 72 registers less across the rotation chains)
