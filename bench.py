@@ -797,7 +797,7 @@ def run_ours(args):
 
 def rollout_line(ctx, args, robots_per_gpu, K):
     """BASELINE config 5: closed-loop horizon -- K Euler-integrated ticks of `robots_per_gpu` robots per GPU, state resident on
-    the device, one fused launch per tick (wbc_rollout)."""
+    the device, the whole horizon in one persistent launch (wbc_rollout)."""
     torch = ctx.torch
     rr, targets = make_robot(ctx, args.robot, robots_per_gpu, args.dt, ALL_TASKS, P2_CONS, True, args.seed + 50 + 1000 * ctx.rank, args.sigma,
                              standing=True)

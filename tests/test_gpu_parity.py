@@ -281,7 +281,7 @@ def test_closed_loop_rollout_matches_oracle():
     mem0, ref0 = robot._mem.clone().cpu().numpy(), robot._ref.clone().cpu().numpy()
     qh, vh, sh = robot.rollout(traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18], record=True)
     assert (sh == 0).all()
-    # the single-call C-ABI rollout (wbc_rollout: K launches, state advanced in place) lands on the same state
+    # the single-call C-ABI rollout (wbc_rollout: one persistent launch for the horizon, state advanced in place) lands on the same state
     twin = _robot(name, N, P1_TASKS, P2_CONS, True)
     twin.current_joint_config = torch.as_tensor(q, device="cuda:0").clone()
     twin._mem.copy_(torch.as_tensor(mem0, device="cuda:0")); twin._ref.copy_(torch.as_tensor(ref0, device="cuda:0"))
