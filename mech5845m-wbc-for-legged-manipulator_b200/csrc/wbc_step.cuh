@@ -652,6 +652,14 @@ __device__ __forceinline__ void warp_kin_a(uint32_t M_a, uint32_t q_a, uint32_t 
 #ifndef WBC_SYNC_PREQP
 #define WBC_SYNC_PREQP 1       // phase barrier before the QP
 #endif
+// Reduced-front instantiations (round 2): with their hot code down from 25 k to 21 k instructions the three barriers in front
+// of the QP cost more than the re-alignment they buy -- the warps of a group leave the barrier after the QP together and stay
+// close enough until the next one: device-resident +2.5 %, closed-loop host tick +0.6 %, config 5 +2.3 %.  The barrier
+// after the QP stays (without it the closed-loop tick loses 9 %), and the general instantiations keep all four (bootstrap P1
+// loses 2.6 % without the front three).
+#ifndef WBC_SYNC_FRONT_RED
+#define WBC_SYNC_FRONT_RED 0
+#endif
 #ifndef WBC_SYNC_POSTQP
 #define WBC_SYNC_POSTQP 1      // phase barrier after the QP
 #endif
@@ -677,6 +685,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
   constexpr StepLayout L = step_layout(NV, WBC_MAX_NC, RED);
   static_assert(NV + 1 <= WBC_IN_IMU, "the IMU quaternion sits behind q inside the q slot");
   constexpr bool PS = WBC_PHASE_SYNC && !DEBUG_OUT;
+  constexpr bool PSF = PS && (!RED || WBC_SYNC_FRONT_RED);     // the three barriers in front of the QP
   constexpr int LD = NV | 1;
   constexpr int nq = NV + 1;
   const int lane = threadIdx.x & 31;
@@ -750,7 +759,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     }
     if (DEBUG_OUT && !valid) break;                      // (after the waits: no copy may be in flight when the CTA exits)
     if (P.f32_in) widen_inputs<NV>(P, in_a, lane);       // (uniform) optional FP32 I/O
-    phase_sync<PS && (WBC_SYNC_TOP != 0)>();
+    phase_sync<PSF && (WBC_SYNC_TOP != 0)>();
     // the next state's inputs travel while this tick computes: the other buffer is free (its last reader was the tail
     // of the previous tick), and a whole tick -- ~20 us per warp -- hides the latency even of a PCIe read (zero-copy
     // host buffers).  Issued here, not in front of the QP, so that its address arithmetic does not sit in the kernel's
@@ -779,7 +788,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     double Sc[6];                        // column `lane` of data.J (WORLD): [lin; ang]
     double com_w[3], Jcom[2];
     warp_kin_a<NV>(M_a, q_a, omi_a, omf_a, lane, (cfg.constraint_mask & WBC_CON_COM) != 0, Sc, com_w, Jcom);
-    phase_sync<PS && (WBC_SYNC_KIN != 0)>();
+    phase_sync<PSF && (WBC_SYNC_KIN != 0)>();
 
     // ---------------------------------------------------------------- task rows for my column (registers)
     // EE tasks: A = W (J_LWA w) (:476-482); trunk task: A = (W J_WORLD) w (:488-490)
@@ -1149,7 +1158,7 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     }
 
     if (!RED) constraint_rows();
-    phase_sync<PS && (WBC_SYNC_PREQP != 0)>();
+    phase_sync<PSF && (WBC_SYNC_PREQP != 0)>();
     const double clb_r = (DEBUG_OUT && lane < nC) ? lds_f64(clb_a + 8 * lane) : 0.0;
     const double cub_r = (DEBUG_OUT && lane < nC) ? lds_f64(cub_a + 8 * lane) : 0.0;
 
