@@ -1237,17 +1237,22 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
     if (P.io.q_next) {
       __syncwarp();
       const double v = x * dt;
-      double vb[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) vb[i] = __shfl_sync(WBC_FULL_MASK, v, i);
       const uint32_t qn_a = ws_a + 8 * L.col;          // [<= 33] new configuration (the 64-double column buffer is free now)
-      if (lane == 0) {
-        double q7[7], o7[7];
+      // (runWBC with IMU feedback keeps nothing of the integrated free-flyer pose: updateState(running=True) puts the old xyz
+      //  and the IMU quaternion in its place and re-estimates xyz (:387-428) -- ~250 serial instructions of lane 0 skipped)
+      const bool need_ff = (P.flags & WBC_STEP_FLAG_PLAIN_INTEGRATE) || !P.io.imu_quat;
+      if (need_ff) {                                   // (uniform)
+        double vb[6];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) q7[i] = lds_f64(q_a + 8 * i);
-        integrate_freeflyer(q7, vb, o7);
+        for (int i = 0; i < 6; ++i) vb[i] = __shfl_sync(WBC_FULL_MASK, v, i);
+        if (lane == 0) {
+          double q7[7], o7[7];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) sts_f64(qn_a + 8 * i, o7[i]);
+          for (int i = 0; i < 7; ++i) q7[i] = lds_f64(q_a + 8 * i);
+          integrate_freeflyer(q7, vb, o7);
+#pragma unroll
+          for (int i = 0; i < 7; ++i) sts_f64(qn_a + 8 * i, o7[i]);
+        }
       }
       if (lane >= 6 && lane < NV) {
         const int iq = lds_s32(M_a + WBC_MOFF(col_q) + 4 * lane);
