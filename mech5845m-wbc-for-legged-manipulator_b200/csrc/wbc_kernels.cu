@@ -603,10 +603,11 @@ static int launch_step_k(const WbcModel* model, const StepParams& P, cudaStream_
   int max_optin = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, model->device));
   constexpr int ctas = StepWarps<SPLIT, RED>::ctas;
-  int warps = (int)(((size_t)(max_optin + 1024) / ctas - 1024 - model_smem_bytes()) / per_warp);
+  const size_t extra = RED ? WBC_GROUP_REPORT_BYTES : 0;      // CTA-shared group-report slots (StepParams::group_report)
+  int warps = (int)(((size_t)(max_optin + 1024) / ctas - 1024 - model_smem_bytes() - extra) / per_warp);
   if (warps > StepWarps<SPLIT, RED>::value) warps = StepWarps<SPLIT, RED>::value;
   if (warps < 1) return fail(WBC_ERR_UNSUPPORTED, "shared memory too small for one state%s");
-  const size_t smem = model_smem_bytes() + warps * per_warp;
+  const size_t smem = model_smem_bytes() + warps * per_warp + extra;
   auto kern = wbc_step_kernel<NV, DBG, SPLIT, FD, NF, RED, MULTI>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long need = (P.N + warps - 1) / warps;
@@ -767,6 +768,7 @@ static int check_cfg(const WbcModel* model, const WbcConfig* cfg, const WbcStepI
   // where the per-tick inputs come out of pinned host memory (+4.7 % end to end)
   P->bulk_in = 0;
   P->K = 1;
+  P->group_report = 0;
   if (io->joint_targets && !io->q_next) return fail(WBC_ERR_INVALID_ARG, "joint_targets needs q_next%s");
   set_reduced(model->host, P);
   return WBC_OK;
@@ -1019,6 +1021,7 @@ int wbc_step_host(WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io, co
       // by the TMA engine (cp.async.bulk + mbarrier); the open-loop call, whose q rows travel by cp.async next to them,
       // measured 9 % slower with it and keeps cp.async (set_bulk() drops what is not float64 / 16-byte aligned)
       if (io->q_next) P.bulk_in = WBC_BULK_TARGETS | WBC_BULK_MEM | WBC_BULK_REF | WBC_BULK_IMU;
+      P.group_report = (host->status || host->iters) ? 1 : 0;   // 4-byte stores over PCIe: one per barrier group, not one per warp
       P.N = N;
       rc = launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
       if (rc == WBC_OK && tune_end) CUDA_TRY(cudaEventRecord(tune_end, (cudaStream_t)stream));

@@ -93,7 +93,12 @@ struct StepParams {
   // closed-loop horizon in ONE launch (the MULTI instantiation, wbc_rollout): K ticks; io.targets / io.imu_quat are then
   // trajectories [K, N, 18] / [K, N, 4], q and the task memory are advanced in place (io.q_next == io.q, io.mem_out == io.mem_in)
   int K;
+  // zero-copy host call: the first warp of each barrier group writes the status / iteration count of the group's (consecutive)
+  // states in one coalesced store behind the post-QP barrier, instead of one 4-byte store per warp -- over PCIe every store
+  // is a transaction of its own, and 110 M four-byte writes per second cost the closed-loop host tick 9 %
+  int group_report;
 };
+#define WBC_GROUP_REPORT_BYTES 512   // CTA-shared: [2 parities][32 warps] status + the same for iters (reduced-front instantiations)
 #define WBC_BULK_TARGETS 1
 #define WBC_BULK_MEM 2
 #define WBC_BULK_REF 4
@@ -1203,7 +1208,6 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
                                                                                     x, a, aj, bj);
     }
 
-    phase_sync<PS && (WBC_SYNC_POSTQP != 0)>();
     {
       const int bm = lds_s32(stash_a + 4);
       base = lds_s32(stash_a);
@@ -1211,6 +1215,13 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       mb_phase = (uint32_t)bm >> 1;
       if (MULTI) { tick = lds_s32(stash_b); toff = (long long)tick * NS; }
     }
+    constexpr bool GRP = RED && PS && (WBC_SYNC_POSTQP != 0) && (WBC_SYNC_GROUP < 0);
+    const uint32_t grp_a = ws_a + 8 * L.total * (wpc - warp) + 128 * buf;      // behind the last warp's workspace; slots alternate
+    if (GRP && P.group_report && lane == 0) {
+      sts_s32(grp_a + 4 * warp, res.status);
+      sts_s32(grp_a + 256 + 4 * warp, res.iters);
+    }
+    phase_sync<PS && (WBC_SYNC_POSTQP != 0)>();
     {   // (scope of the re-derived loop state: it shadows what the first half of the tick used)
     int sidx_p = base + warp;
     const bool valid = sidx_p < NS;
@@ -1222,9 +1233,20 @@ __device__ __forceinline__ void warp_wbc_states(const StepParams& P, const DevMo
       if (P.f32_out & WBC_F32_QDOT) reinterpret_cast<float*>(P.io.qdot)[sidx * NV + lane] = (float)x;
       else P.io.qdot[sidx * NV + lane] = x;
     }
+    if (GRP && P.group_report) {
+      const int half = (wpc + 1) >> 1;
+      const int g0 = warp >= half ? half : 0, gn = warp >= half ? wpc - half : half;
+      const int sg = base + g0 + lane;
+      if (warp == g0 && lane < gn && sg < NS) {
+        P.io.status[sg] = lds_s32(grp_a + 4 * (g0 + lane));
+        P.io.iters[sg] = lds_s32(grp_a + 256 + 4 * (g0 + lane));
+      }
+    }
     if (valid && lane == 0) {
-      P.io.status[sidx] = res.status;
-      P.io.iters[sidx] = res.iters;
+      if (!(GRP && P.group_report)) {
+        P.io.status[sidx] = res.status;
+        P.io.iters[sidx] = res.iters;
+      }
       if (P.io.active_set) {
         P.io.active_set[2 * sidx] = res.act_box;
         P.io.active_set[2 * sidx + 1] = res.act_rows;
