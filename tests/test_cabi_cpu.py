@@ -209,3 +209,27 @@ def test_standing_sampler_and_config3_rows():
     assert len(rows) == 23 and all(len(r[2]) == 6 for r in rows)
     assert [r[0] for r in rows[:16]] == [f for f in range(4) for _ in range(4)] and all(r[4] == 0.0 for r in rows[:16])
     assert all(r[3] == -r[4] and r[4] > 0 for r in rows[16:])
+
+
+def build_c_demo(out_dir):
+    """gcc (C11, no CUDA compiler, no Python, no torch) -> examples/c_abi_demo linked against libwbc_b200.so + libcudart."""
+    from wbc_b200 import _cabi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = os.path.join(str(out_dir), "c_abi_demo")
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.run(["gcc", "-O2", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(root, "examples", "c_abi_demo.c"), "-o", exe, "-L", libdir, "-lwbc_b200",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"],
+                   check=True)
+    return exe
+
+
+def test_c_program_compiles_and_links_against_the_abi(lib, tmp_path):
+    """The boundary is usable from plain C: examples/c_abi_demo.c (one batched runWBC tick through wbc_model_create + wbc_step)
+    compiles with gcc -std=c11 -Wall -Werror against include/wbc_b200.h and links against the shared library.  (It runs in
+    tests/test_gpu_surface.py::test_c_abi_demo_matches_python_path.)"""
+    exe = build_c_demo(tmp_path)
+    assert os.path.exists(exe)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 1 and "usage" in out.stderr            # argument check only: no device is touched

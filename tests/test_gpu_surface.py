@@ -611,3 +611,41 @@ def test_fp32_host_io_mode_agrees_with_fp64():
         assert ok.double().mean() > 0.99
         dv = (hout["qdot"].double()[ok] - x64.cpu()[ok]).abs()
         assert dv.max() < 5e-2 and dv.median() < 1e-3, (chunks, float(dv.max()), float(dv.median()))
+
+
+# ------------------------------------------------------------------------------------------------ the boundary from plain C
+def test_c_abi_demo_matches_python_path(tmp_path):
+    """examples/c_abi_demo.c -- a C11 program with no Python and no torch in it -- runs one batched runWBC tick through
+    wbc_model_create + wbc_step on the arrays of a case file and must return, bit for bit, what the Python mirror returns for
+    the same states: the drop-in boundary is the C ABI, not the Python on top of it."""
+    import ctypes as C
+    import struct
+    import subprocess
+    from tests.test_cabi_cpu import build_c_demo
+    name, N = "a1_wx200", 3000
+    robot = _robot(name, N, P1_TASKS, P2_CONS, True)
+    q, targets = _load(robot, N, 20260071, 5e-4)
+    mem0, ref0 = robot._mem.clone(), robot._ref.clone()
+    case, result = tmp_path / "case.bin", tmp_path / "result.bin"
+    table, cfg = robot._table, robot._config()
+    with open(case, "wb") as f:
+        f.write(struct.pack("<qqd", 0x57424332, N, float(robot.dt)))
+        f.write(struct.pack("<q", C.sizeof(table))); f.write(bytes(table))
+        f.write(struct.pack("<q", C.sizeof(cfg))); f.write(bytes(cfg))
+        for a in (robot.current_joint_config, targets, mem0, ref0):
+            f.write(a.detach().cpu().contiguous().numpy().tobytes())
+    exe = build_c_demo(tmp_path)
+    out = subprocess.run([exe, str(case), str(result)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    print(out.stdout.strip())
+    nq, nv = robot.n_configuration_dimensions, robot.n_velocity_dimensions
+    raw = np.fromfile(result, dtype=np.uint8)
+    o = 0
+    qdot_c = raw[o:o + N * nv * 8].view(np.float64).reshape(N, nv); o += N * nv * 8
+    qn_c = raw[o:o + N * nq * 8].view(np.float64).reshape(N, nq); o += N * nq * 8
+    st_c = raw[o:o + N * 4].view(np.int32); o += N * 4
+    it_c = raw[o:o + N * 4].view(np.int32)
+    x = robot.step(targets[:, :15].reshape(N, 5, 3), targets[:, 15:18], advance=True)
+    assert (st_c == 0).all()
+    assert np.array_equal(qdot_c, _np(x)) and np.array_equal(qn_c, _np(robot.current_joint_config))
+    assert np.array_equal(st_c, _np(robot.last_status)) and np.array_equal(it_c, _np(robot.last_iters))
