@@ -675,6 +675,8 @@ def run_ours(args):
             configs.append(config_line(ctx, "P3 stress", "a1_wx200", n_local, args.dt, ALL_TASKS, P2_CONS, True, 20260006, 5e-3, b,
                                        what="the headline step with 10x the target noise: bounds and the trunk box bind"))
         configs.append(rollout_line(ctx, args, 16384, 100))
+        if world == 1:
+            configs.append(rollout_line(ctx, args, 16384, 40, sim3=True))
 
     # ---- verification gather (off the timed path): NCCL all_gather of solutions / status -------------
     reset_state()
@@ -795,12 +797,18 @@ def run_ours(args):
     return 0
 
 
-def rollout_line(ctx, args, robots_per_gpu, K):
+def rollout_line(ctx, args, robots_per_gpu, K, sim3=False):
     """BASELINE config 5: closed-loop horizon -- K Euler-integrated ticks of `robots_per_gpu` robots per GPU, state resident on
-    the device, the whole horizon in one persistent launch (wbc_rollout)."""
+    the device, the whole horizon in one persistent launch (wbc_rollout).  `sim3`: the controller settings of the reference's
+    own driver (sim3.py:145-148: A1+PX100, gripper task + "HYBRID" joint task, trunk / feet constraints) instead of the full
+    task stack."""
     torch = ctx.torch
-    rr, targets = make_robot(ctx, args.robot, robots_per_gpu, args.dt, ALL_TASKS, P2_CONS, True, args.seed + 50 + 1000 * ctx.rank, args.sigma,
-                             standing=True)
+    if sim3:
+        rr, targets = make_robot(ctx, "a1_px100_pin_ver", robots_per_gpu, args.dt, GRIP_TASK, P2_CONS, "HYBRID",
+                                 args.seed + 60 + 1000 * ctx.rank, args.sigma, standing=True)
+    else:
+        rr, targets = make_robot(ctx, args.robot, robots_per_gpu, args.dt, ALL_TASKS, P2_CONS, True, args.seed + 50 + 1000 * ctx.rank,
+                                 args.sigma, standing=True)
     if args.rollout_max_iter > 0:
         rr.max_qp_iterations = args.rollout_max_iter
     q0, mem0 = rr.current_joint_config.clone(), rr._mem.clone()
@@ -821,11 +829,14 @@ def rollout_line(ctx, args, robots_per_gpu, K):
         ctx.barrier()
         ms = ctx.max_ms(r0.elapsed_time(r1))
         best = ms if best is None else min(best, ms)
-    return {"config": "configs[4]", "what": f"closed-loop rollout: {K} Euler-integrated WBC ticks over {n} robots per GPU, task memory and "
+    return {"config": "sim3 closed loop (HYBRID)" if sim3 else "configs[4]",
+            "what": ("the tick loop of sim3.py:287-327 with its own controller settings (gripper task + HYBRID joint task: 12 finite-"
+                     "difference FK passes per tick), " if sim3 else "") +
+                    f"closed-loop rollout: {K} Euler-integrated WBC ticks over {n} robots per GPU, task memory and "
                                             "configuration advanced in place on the device, the whole horizon in ONE persistent launch (a robot stays with "
                                             "one warp for all ticks: no relaunch and no drain tail per tick); standing-pose "
                                             "sampler (near-level trunk: the reference's base estimator presupposes it, quirk D.10)",
-            "robot": args.robot, "states_per_gpu": n, "ticks": K, "robots": n * ctx.world,
+            "robot": "a1_px100_pin_ver" if sim3 else args.robot, "states_per_gpu": n, "ticks": K, "robots": n * ctx.world,
             "steps_per_s": n * ctx.world * K / (best * 1e-3), "ms_per_tick": best / K,
             "qp_iteration_cap": rr.max_qp_iterations,
             "solved_fraction_last_tick": float((rr.last_status == 0).double().mean().item()),

@@ -301,7 +301,7 @@ int wbc_step_host_path(const WbcModel* model);
 
 /* Closed loop: K consecutive ticks (the tick loop of sim3.py:287-327 around runWBC, Robot_Wrapper4.py:1330-1412) for
  * N robots, configuration and task memory advanced in place on the device.  With the usual constraint set (trunk box + four
- * feet, <= 16 rows, joint task ZERO / PREV) the whole horizon is ONE persistent launch: a robot stays with one warp for
+ * feet, <= 16 rows, any joint-task mode) the whole horizon is ONE persistent launch: a robot stays with one warp for
  * all K ticks, so the ticks need no grid-wide synchronisation and only the last one has a drain tail; every other
  * configuration runs one fused launch per tick.  Results are identical either way.
  * io->q is read and overwritten (io->q_next must be NULL or equal to io->q), io->mem_in likewise (io->mem_out NULL or

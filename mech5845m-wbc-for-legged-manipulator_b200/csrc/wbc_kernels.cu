@@ -641,8 +641,9 @@ static int launch_step_t(const WbcModel* model, const StepParams& P, cudaStream_
       // the twelve foot equality rows eliminated up front (wbc_qp_red.inc) when model and configuration allow it
       // (also with the finite-difference joint task, "MANI" / "HYBRID": what sim3.py:145-148 runs)
       if constexpr (!DBG) {
-        // the whole closed-loop horizon in one launch (wbc_rollout; the usual joint-task modes only)
-        if (P.red_ok && !fd && P.K > 1) return launch_step_k<NV, DBG, true, false, 3, true, true>(model, P, st, info);
+        // the whole closed-loop horizon in one launch (wbc_rollout)
+        if (P.red_ok && P.K > 1) return fd ? launch_step_k<NV, DBG, true, true, 3, true, true>(model, P, st, info)
+                                           : launch_step_k<NV, DBG, true, false, 3, true, true>(model, P, st, info);
         if (P.red_ok) return fd ? launch_step_k<NV, DBG, true, true, 3, true>(model, P, st, info)
                                 : launch_step_k<NV, DBG, true, false, 3, true>(model, P, st, info);
       }
@@ -1129,13 +1130,12 @@ int wbc_rollout(const WbcModel* model, const WbcConfig* cfg, const WbcStepIO* io
   int rc = check_cfg(model, cfg, &tick, &P);
   if (rc != WBC_OK) return rc;
   P.N = N;
-  // The whole horizon in ONE launch where the reduced-front instantiation applies (four foot constraints, <= 16 rows, the
-  // usual joint-task modes): a robot stays with one warp for all K ticks, so nothing separates the ticks but that warp's own
+  // The whole horizon in ONE launch where the reduced-front instantiation applies (four foot constraints, <= 16 rows, any
+  // joint-task mode): a robot stays with one warp for all K ticks, so nothing separates the ticks but that warp's own
   // program order -- no relaunch, no drain tail per tick.  WBC_B200_ROLLOUT_LAUNCHES=1 forces one launch per tick (A/B runs).
   static const bool per_tick = [] { const char* e = getenv("WBC_B200_ROLLOUT_LAUNCHES"); return e && e[0] == '1'; }();
-  const bool fd = (P.cfg.task_mask & WBC_TASK_JOINT) && (P.cfg.joint_mode == WBC_JOINT_MANI || P.cfg.joint_mode == WBC_JOINT_HYBRID);
   const bool locked3 = model->host.nv - (P.cfg.gripper_joint_id - 2 + 6) == 3;
-  if (K > 1 && !per_tick && P.red_ok && P.nC <= 16 && locked3 && !fd && (model->host.nv == 25 || model->host.nv == 26)) {
+  if (K > 1 && !per_tick && P.red_ok && P.nC <= 16 && locked3 && (model->host.nv == 25 || model->host.nv == 26)) {
     P.K = K;
     return launch_step<false>(model, P, (cudaStream_t)stream, nullptr);
   }

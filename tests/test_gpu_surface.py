@@ -543,6 +543,27 @@ def test_rollout_in_one_launch_equals_tick_by_tick(name, N, K):
         assert torch.equal(robot._ref, ref0)
 
 
+@pytest.mark.parametrize("joint", ["HYBRID", "MANI"])
+def test_rollout_in_one_launch_finite_difference_joint_task(joint):
+    """The closed loop `sim3.py` actually runs (gripper task + "HYBRID" joint task + trunk / feet constraints, sim3.py:145-148
+    inside the tick loop :287-327) as one persistent launch: bit for bit where the tick-by-tick launches land -- including the
+    reference's perturbed-state quirk of the finite-difference modes (the configuration the tick integrates from is the
+    perturbed one), which the next tick of the same launch has to see."""
+    name, N, K = "a1_px100_pin_ver", 700, 5
+    robot = _robot(name, N, P2_TASKS, P2_CONS, joint)
+    q, targets = _load(robot, N, 20260073, 5e-4)
+    q0, mem0 = robot.current_joint_config.clone(), robot._mem.clone()
+    gen = torch.Generator(device=DEV); gen.manual_seed(13)
+    traj = targets[None] + torch.randn(K, N, 18, dtype=torch.float64, device=DEV, generator=gen).mul_(2e-4).cumsum(0)
+    ee, tr = traj[:, :, :15].reshape(K, N, 5, 3), traj[:, :, 15:18]
+    qh, vh, sh = robot.rollout(ee, tr, record=True)
+    mem_end, it_end = robot._mem.clone(), robot.last_iters.clone()
+    robot.current_joint_config = q0.clone(); robot._mem.copy_(mem0)
+    v = robot.rollout(ee, tr)
+    assert torch.equal(robot.current_joint_config, qh[-1]) and torch.equal(v, vh[-1])
+    assert torch.equal(robot.last_status, sh[-1]) and torch.equal(robot._mem, mem_end) and torch.equal(robot.last_iters, it_end)
+
+
 def test_fp32_host_io_mode_agrees_with_fp64():
     """The optional FP32 I/O mode (north_star: "an optional FP32 mode must agree within 1e-4"): float32 arrays on the
     host side, float64 arithmetic in the tick.  Closed loop over several ticks against the float64 call on the same data:
